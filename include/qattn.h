@@ -1,0 +1,102 @@
+/* qattn.h - C ABI of the B200-native FP8 fused-attention library (libqattn_sm100.so).
+ *
+ * This is the drop-in boundary for the hot path of WaveSpeedAI/QuantumAttention: everything below the Python
+ * functions `fp8_attn_func` / `fp8_token_wise_attn_func` / `dynamically_quantize_fp8`.  The reference has no C
+ * ABI; its boundary is a JIT-built torch extension exposing
+ *     attention_forward(q, k, v[, scale_q, scale_k], causal) -> [o]
+ * (reference: src/quantum_attn/tk/attention.py:355-360, launcher :362-647) plus Inductor-generated quantise kernels
+ * (reference: src/quantum_attn/nn.py:14-19, 410-418).  Each entry point below cites what it replaces.
+ *
+ * Conventions
+ *   - plain pointers to DEVICE memory, sizes as int, no torch types; the caller owns every buffer
+ *   - every call is asynchronous on the given stream; no host sync, no allocation inside the library
+ *   - return value: 0 = ok, negative = error (see QA_ERR_*); text via qa_last_error() (thread-local)
+ *   - tensors are [B, H, S, D]; quantised tensors are DENSE ([B,H,S,D] contiguous, 1 byte per element, e4m3fn)
+ *   - the library requires an sm_100 device; there is no fallback path
+ */
+#ifndef QATTN_H_
+#define QATTN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QA_ABI_VERSION 1
+
+/* element types */
+#define QA_DT_BF16 0
+#define QA_DT_FP16 1
+#define QA_DT_E4M3 2
+
+/* scale granularity (reference: "head-wise" src/quantum_attn/nn.py:411-412, "token-wise" :413-414) */
+#define QA_SCALE_HEAD 0  /* one fp32 scale per (b, h):        scale[B*H]     */
+#define QA_SCALE_TOKEN 1 /* one fp32 scale per (b, h, token): scale[B*H*S]   */
+
+/* how P = softmax(QK^T) is fed to the second GEMM */
+#define QA_P_E4M3 0      /* P -> e4m3, V e4m3, tcgen05 kind::f8f6f4               (north-star fast path)          */
+#define QA_P_E4M3_HILO 1 /* P -> e4m3 hi + e4m3 lo (two MMAs), V e4m3            (accurate FP8 path)             */
+#define QA_P_16BIT 2     /* P -> bf16/fp16, V unquantised 16-bit, kind::f16       (the reference's own numerics:  */
+                         /*                                   src/quantum_attn/tk/attention.py:230,286,318)      */
+
+/* error codes */
+#define QA_OK 0
+#define QA_ERR_INVALID (-1)     /* bad argument / unsupported shape */
+#define QA_ERR_DEVICE (-2)      /* device is not sm_100, or driver entry point missing */
+#define QA_ERR_CUDA (-3)        /* CUDA runtime error at launch */
+#define QA_ERR_UNSUPPORTED (-4) /* valid request this build does not implement yet */
+
+int qa_abi_version(void);
+const char* qa_last_error(void);
+
+/* 1 if device `dev` can run the kernels (compute capability 10.x), else 0 (and qa_last_error says why).
+ * Replaces the reference's capability gate (src/quantum_attn/nn.py:208-216), which accepts >= 9.0 although its
+ * kernel only exists for sm_90a. */
+int qa_device_supported(int dev);
+
+/* Dynamic FP8 quantisation, one launch pair for up to 3 tensors of the same [B,H,*,D] family.
+ *   scale = max(amax(|x|) * (1/448), FLT_EPSILON);  x8 = e4m3_rne(clamp(x / scale, +-448))   (all fp32, IEEE division)
+ * Replaces the Inductor-generated kernels of `_dynamically_quantize_fp8` (reference: src/quantum_attn/nn.py:14-19).
+ *
+ *   n_tensors   1..3
+ *   x[i]        device pointer, dtype x_dtype (QA_DT_BF16 / QA_DT_FP16), logical shape [B, H, S[i], D]
+ *   x_strides   4 element strides per tensor (x_strides[4*i .. 4*i+3]); the last one must be 1, rows 16-byte aligned
+ *   x8[i]       out: dense e4m3 bytes [B, H, S[i], D]
+ *   scale[i]    out: fp32 [B*H] (QA_SCALE_HEAD) or [B*H*S[i]] (QA_SCALE_TOKEN)
+ *   amax_ws     scratch, 3 * B * H floats (QA_SCALE_HEAD only; may be NULL for token mode); need not be zeroed
+ */
+int qa_quantize_fp8(int n_tensors, const void* const* x, int x_dtype, const int64_t* x_strides, void* const* x8,
+                    float* const* scale, float* amax_ws, int B, int H, const int* S, int D, int scale_mode,
+                    void* stream);
+
+/* Fused QK^T -> online softmax -> PV forward on quantised inputs.
+ * Replaces `attention_forward` of the reference's TK module (src/quantum_attn/tk/attention.py:355-647) and the kernel
+ * it launches (`fwd_attend_ker`, :97-349), and defines the same function as the op
+ * `quantum_attn::fp8_attention_forward` (src/quantum_attn/ops.py:64-95):
+ *     out = softmax(sm_scale * (q8*scale_q)(k8*scale_k)^T  [+ top-left causal mask]) (v*scale_v)
+ *
+ *   q8, k8      dense e4m3 [B,Hq,Sq,D], [B,Hkv,Skv,D]
+ *   v           QA_P_E4M3 / QA_P_E4M3_HILO: dense e4m3 [B,Hkv,Skv,D] with scale_v[B*Hkv] (head-wise)
+ *               QA_P_16BIT: dense bf16/fp16 (v_dtype) [B,Hkv,Skv,D], scale_v may be NULL
+ *   scale_q/k   fp32, layout per scale_mode (token mode: scale_q[B*Hq*Sq], scale_k[B*Hkv*Skv])
+ *   out         dense [B,Hq,Sq,D] of out_dtype (QA_DT_BF16 / QA_DT_FP16)
+ *   lse         optional fp32 [B*Hq*Sq]: natural-log sum-exp of the scaled scores per row (for merging partial
+ *               results across sequence shards); NULL to skip.  The reference leaves this output commented out
+ *               (src/quantum_attn/tk/attention.py:333-346).
+ *   sm_scale    softmax scale; pass 1/sqrt(D) for the reference's behaviour (src/quantum_attn/tk/attention.py:208-210)
+ *   Hq % Hkv == 0 (GQA: kv head = q head / (Hq/Hkv)); D in {64, 128, 256}; causal mask is top-left aligned.
+ */
+int qa_fp8_attn_fwd(const void* q8, const void* k8, const void* v, int v_dtype, const float* scale_q,
+                    const float* scale_k, const float* scale_v, int scale_mode, void* out, int out_dtype, float* lse,
+                    int B, int Hq, int Hkv, int Sq, int Skv, int D, int causal, float sm_scale, int p_mode,
+                    void* stream);
+
+/* Number of kernels the previous call on this thread launched (for bench.py's gpu_launches accounting). */
+int qa_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QATTN_H_ */

@@ -1,0 +1,165 @@
+"""ctypes binding of the C ABI in include/qattn.h.  PyTorch only supplies device memory and the current stream.
+
+There is NO fallback: if the shared library is missing or the device is not sm_100 the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import build as _build
+
+QA_DT_BF16, QA_DT_FP16, QA_DT_E4M3 = 0, 1, 2
+QA_SCALE_HEAD, QA_SCALE_TOKEN = 0, 1
+QA_P_E4M3, QA_P_E4M3_HILO, QA_P_16BIT = 0, 1, 2
+ABI_VERSION = 1
+
+EXPORTED_SYMBOLS = (
+    "qa_abi_version",
+    "qa_last_error",
+    "qa_device_supported",
+    "qa_quantize_fp8",
+    "qa_fp8_attn_fwd",
+    "qa_last_launch_count",
+)
+
+_lib = None
+_lock = threading.Lock()
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load(build_if_missing: bool = True):
+    """Load (building first if the .so is absent and nvcc is available).  Raises if it cannot be loaded."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        path = lib_path()
+        if not os.path.exists(path):
+            if not build_if_missing:
+                raise NativeError(f"{path} is missing; run `python -m quantumattention_b200.build`")
+            _build.build_library()
+        lib = ctypes.CDLL(path)
+        lib.qa_abi_version.restype = ctypes.c_int
+        lib.qa_last_error.restype = ctypes.c_char_p
+        lib.qa_last_launch_count.restype = ctypes.c_int
+        lib.qa_device_supported.argtypes = [ctypes.c_int]
+        lib.qa_device_supported.restype = ctypes.c_int
+        vp = ctypes.c_void_p
+        lib.qa_quantize_fp8.argtypes = [
+            ctypes.c_int, ctypes.POINTER(vp), ctypes.c_int, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(vp),
+            ctypes.POINTER(vp), vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.c_int,
+            ctypes.c_int, vp,
+        ]
+        lib.qa_quantize_fp8.restype = ctypes.c_int
+        lib.qa_fp8_attn_fwd.argtypes = [
+            vp, vp, vp, ctypes.c_int, vp, vp, vp, ctypes.c_int, vp, ctypes.c_int, vp,
+            ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+            ctypes.c_float, ctypes.c_int, vp,
+        ]
+        lib.qa_fp8_attn_fwd.restype = ctypes.c_int
+        if lib.qa_abi_version() != ABI_VERSION:
+            raise NativeError(f"ABI mismatch: library {lib.qa_abi_version()} != binding {ABI_VERSION}")
+        _lib = lib
+    return _lib
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        msg = load().qa_last_error().decode("utf-8", "replace")
+        if rc == -1:
+            raise ValueError(f"{what}: {msg}")
+        raise NativeError(f"{what} failed (code {rc}): {msg}")
+
+
+def _dt_code(dtype: torch.dtype) -> int:
+    if dtype == torch.bfloat16:
+        return QA_DT_BF16
+    if dtype == torch.float16:
+        return QA_DT_FP16
+    if dtype == torch.float8_e4m3fn:
+        return QA_DT_E4M3
+    raise ValueError(f"unsupported dtype {dtype}")
+
+
+def last_launch_count() -> int:
+    return int(load().qa_last_launch_count())
+
+
+def quantize_fp8(tensors: Sequence[torch.Tensor], scale_mode: int) -> Tuple[list, list]:
+    """Quantise 1-3 CUDA tensors [B,H,S_i,D] (bf16/fp16, same B,H,D,dtype) in one launch pair.
+
+    Returns ([e4m3 tensors], [fp32 scales: [B,H] head-wise or [B,H,S_i] token-wise]).
+    """
+    lib = load()
+    n = len(tensors)
+    t0 = tensors[0]
+    B, H, _, D = t0.shape
+    dev = t0.device
+    xs = []
+    for t in tensors:
+        if t.device != dev or t.dtype != t0.dtype or t.dim() != 4 or t.shape[0] != B or t.shape[1] != H or t.shape[3] != D:
+            raise ValueError("quantize_fp8: tensors must share device, dtype, B, H and D")
+        if t.stride(3) != 1 or any(s % 8 for s in t.stride()[:3]) or t.data_ptr() % 16:
+            t = t.contiguous()
+        xs.append(t)
+    outs = [torch.empty(t.shape, dtype=torch.float8_e4m3fn, device=dev) for t in xs]
+    if scale_mode == QA_SCALE_HEAD:
+        scales = [torch.empty((B, H), dtype=torch.float32, device=dev) for _ in xs]
+        ws = torch.empty((3 * B * H,), dtype=torch.float32, device=dev)
+        ws_ptr = ws.data_ptr()
+    else:
+        scales = [torch.empty((B, H, t.shape[2]), dtype=torch.float32, device=dev) for t in xs]
+        ws_ptr = None
+    vp = ctypes.c_void_p
+    x_arr = (vp * n)(*[t.data_ptr() for t in xs])
+    o_arr = (vp * n)(*[t.data_ptr() for t in outs])
+    s_arr = (vp * n)(*[t.data_ptr() for t in scales])
+    strides = (ctypes.c_int64 * (4 * n))(*[s for t in xs for s in t.stride()])
+    S = (ctypes.c_int * n)(*[t.shape[2] for t in xs])
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        rc = lib.qa_quantize_fp8(n, x_arr, _dt_code(t0.dtype), strides, o_arr, s_arr, ws_ptr, B, H, S, D,
+                                 scale_mode, stream)
+    _check(rc, "qa_quantize_fp8")
+    return outs, scales
+
+
+def fp8_attn_fwd(q8: torch.Tensor, k8: torch.Tensor, v: torch.Tensor, scale_q: torch.Tensor, scale_k: torch.Tensor,
+                 scale_v: Optional[torch.Tensor], *, scale_mode: int, is_causal: bool, sm_scale: float, p_mode: int,
+                 out_dtype: torch.dtype, return_lse: bool = False):
+    """Launch the fused forward kernel.  q8/k8 dense e4m3 [B,H,S,D]; v dense e4m3 (+scale_v) or bf16/fp16."""
+    lib = load()
+    B, Hq, Sq, D = q8.shape
+    Hkv, Skv = k8.shape[1], k8.shape[2]
+    dev = q8.device
+    q8, k8, v = q8.contiguous(), k8.contiguous(), v.contiguous()
+    scale_q = scale_q.to(torch.float32).contiguous()
+    scale_k = scale_k.to(torch.float32).contiguous()
+    if scale_v is not None:
+        scale_v = scale_v.to(torch.float32).contiguous()
+    out = torch.empty((B, Hq, Sq, D), dtype=out_dtype, device=dev)
+    lse = torch.empty((B, Hq, Sq), dtype=torch.float32, device=dev) if return_lse else None
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        rc = lib.qa_fp8_attn_fwd(
+            q8.data_ptr(), k8.data_ptr(), v.data_ptr(), _dt_code(v.dtype), scale_q.data_ptr(), scale_k.data_ptr(),
+            scale_v.data_ptr() if scale_v is not None else None, scale_mode, out.data_ptr(), _dt_code(out_dtype),
+            lse.data_ptr() if lse is not None else None, B, Hq, Hkv, Sq, Skv, D, int(bool(is_causal)),
+            float(sm_scale), p_mode, stream,
+        )
+    _check(rc, "qa_fp8_attn_fwd")
+    return (out, lse) if return_lse else out

@@ -1,0 +1,56 @@
+"""Run-time flags, patchable with ``config.patch({...})`` exactly like the reference's module config
+(reference: src/quantum_attn/config.py:11-41; the tests toggle ``attention.force_eager_fallback`` through
+``quantum_attn.config.patch``, tests/test_interface.py:45-49).
+
+Flags that steered the reference's Inductor / Triton / ThunderKittens backends are kept as inert names so that callers
+which set them keep working; the B200 build has exactly one backend and no tracing compiler in the hot path.
+"""
+import os
+import sys
+
+_save_config_ignore = set()
+
+
+def _flag(name: str, default: str = "0") -> bool:
+    return os.getenv(name, default) == "1"
+
+
+# inert (reference compatibility): accumulation is always fp32 in TMEM here
+use_fast_accum = _flag("QUANTUM_ATTN_USE_FAST_ACCUM", "1")
+
+
+class dynamo:
+    # inert: nothing is compiled with torch.compile on the B200 path
+    dynamic = _flag("QUANTUM_ATTN_DYNAMIC")
+    mode = os.getenv("QUANTUM_ATTN_MODE", "default")
+
+
+class triton:
+    # inert: there is no Triton backend
+    enable_fast_math = _flag("QUANTUM_ATTN_ENABLE_FAST_MATH", "1")
+    allow_reduced_precision_compute = _flag("QUANTUM_ATTN_ALLOW_REDUCED_PRECISION_COMPUTE")
+
+
+class attention:
+    skip_supported_check = _flag("QUANTUM_ATTN_SKIP_SUPPORTED_CHECK")
+    # Debug switch kept from the reference: evaluate the op's semantic definition (dequantise, then aten SDPA on
+    # the GPU) instead of the sm_100a kernel.  Never taken by default; used by tests as an on-box comparator.
+    force_eager_fallback = _flag("QUANTUM_ATTN_FORCE_EAGER_FALLBACK")
+    # inert backend toggles of the reference
+    enable_tk_tma_kernel = _flag("QUANTUM_ATTN_ENABLE_TK_TMA_KERNEL", "1")
+    enable_triton_tma_kernel = _flag("QUANTUM_ATTN_ENABLE_TRITON_TMA_KERNEL")
+    # B200 build: how P = softmax(QK^T) and V enter the second GEMM.
+    #   "fp8"      P -> e4m3, V -> e4m3 (head-wise scale), tcgen05 kind::f8f6f4            (fastest)
+    #   "fp8_hilo" P -> e4m3 hi + e4m3 lo (two MMAs per K slice), V -> e4m3                (FP8, tight max-abs error)
+    #   "16bit"    P -> bf16/fp16, V unquantised, kind::f16: the reference kernel's own numerics
+    #              (src/quantum_attn/tk/attention.py:230,286,318)
+    pv_mode = os.getenv("QUANTUM_ATTN_PV_MODE", "fp8")
+
+
+try:
+    from torch.utils._config_module import install_config_module
+except ImportError:  # pragma: no cover
+    from torch._dynamo.config_utils import install_config_module
+
+# adds patch(), save_config(), load_config() ...
+install_config_module(sys.modules[__name__])

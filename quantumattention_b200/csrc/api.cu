@@ -1,0 +1,143 @@
+// extern "C" surface of libqattn_sm100.so (declared in include/qattn.h): argument validation, error reporting,
+// and dispatch into the kernels.  No torch types, no allocation, no host synchronisation.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include "qattn_internal.h"
+
+namespace qa {
+
+static thread_local char g_err[512] = "";
+static thread_local int g_launches = 0;
+
+int set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+int set_cuda_error(const char* what, cudaError_t e) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+    return QA_ERR_CUDA;
+}
+
+static int check_device() {
+    int dev = -1;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return set_error(QA_ERR_DEVICE, "no CUDA device: %s", cudaGetErrorString(e));
+    int major = 0;
+    e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (e != cudaSuccess) return set_cuda_error("cudaDeviceGetAttribute", e);
+    if (major != 10)
+        return set_error(QA_ERR_DEVICE, "device %d has compute capability %d.x; this library only runs on sm_100", dev,
+                         major);
+    return QA_OK;
+}
+
+}  // namespace qa
+
+using namespace qa;
+
+extern "C" {
+
+int qa_abi_version(void) { return QA_ABI_VERSION; }
+const char* qa_last_error(void) { return g_err; }
+int qa_last_launch_count(void) { return g_launches; }
+
+int qa_device_supported(int dev) {
+    int major = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (e != cudaSuccess) {
+        set_cuda_error("cudaDeviceGetAttribute", e);
+        return 0;
+    }
+    if (major != 10) {
+        set_error(QA_ERR_DEVICE, "device %d has compute capability %d.x; sm_100 required", dev, major);
+        return 0;
+    }
+    return 1;
+}
+
+int qa_quantize_fp8(int n_tensors, const void* const* x, int x_dtype, const int64_t* x_strides, void* const* x8,
+                    float* const* scale, float* amax_ws, int B, int H, const int* S, int D, int scale_mode,
+                    void* stream) {
+    g_launches = 0;
+    if (n_tensors < 1 || n_tensors > 3) return set_error(QA_ERR_INVALID, "n_tensors must be 1..3, got %d", n_tensors);
+    if (!x || !x_strides || !x8 || !scale || !S) return set_error(QA_ERR_INVALID, "null argument array");
+    if (x_dtype != QA_DT_BF16 && x_dtype != QA_DT_FP16)
+        return set_error(QA_ERR_INVALID, "x_dtype must be bf16 or fp16");
+    if (scale_mode != QA_SCALE_HEAD && scale_mode != QA_SCALE_TOKEN)
+        return set_error(QA_ERR_INVALID, "Unsupported scaling_method code: %d", scale_mode);
+    if (D != 64 && D != 128 && D != 256) return set_error(QA_ERR_INVALID, "Unsupported head dimension: %d", D);
+    if (B < 1 || H < 1 || int64_t(B) * H > 65535) return set_error(QA_ERR_INVALID, "B*H out of range");
+    if (scale_mode == QA_SCALE_HEAD && !amax_ws) return set_error(QA_ERR_INVALID, "amax_ws required for head-wise");
+    QuantArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int i = 0; i < n_tensors; ++i) {
+        if (!x[i] || !x8[i] || !scale[i]) return set_error(QA_ERR_INVALID, "null tensor pointer (tensor %d)", i);
+        if (S[i] < 1) return set_error(QA_ERR_INVALID, "empty sequence (tensor %d)", i);
+        const int64_t* st = x_strides + 4 * i;
+        if (st[3] != 1) return set_error(QA_ERR_INVALID, "last-dim stride must be 1 (tensor %d)", i);
+        if ((reinterpret_cast<uintptr_t>(x[i]) & 15) || (st[0] & 7) || (st[1] & 7) || (st[2] & 7))
+            return set_error(QA_ERR_INVALID, "rows must be 16-byte aligned (tensor %d)", i);
+        if (reinterpret_cast<uintptr_t>(x8[i]) & 15) return set_error(QA_ERR_INVALID, "x8 must be 16-byte aligned");
+        a.x[i] = x[i];
+        a.x8[i] = x8[i];
+        a.scale[i] = scale[i];
+        for (int d = 0; d < 4; ++d) a.strides[i][d] = st[d];
+        a.S[i] = S[i];
+    }
+    a.B = B, a.H = H, a.D = D;
+    a.amax_ws = amax_ws;
+    int rc = check_device();
+    if (rc != QA_OK) return rc;
+    return quantize_dispatch(a, x_dtype, scale_mode, n_tensors, static_cast<cudaStream_t>(stream), &g_launches);
+}
+
+int qa_fp8_attn_fwd(const void* q8, const void* k8, const void* v, int v_dtype, const float* scale_q,
+                    const float* scale_k, const float* scale_v, int scale_mode, void* out, int out_dtype, float* lse,
+                    int B, int Hq, int Hkv, int Sq, int Skv, int D, int causal, float sm_scale, int p_mode,
+                    void* stream) {
+    g_launches = 0;
+    if (!q8 || !k8 || !v || !scale_q || !scale_k || !out) return set_error(QA_ERR_INVALID, "null pointer argument");
+    if (D != 64 && D != 128 && D != 256) return set_error(QA_ERR_INVALID, "Unsupported head dimension: %d", D);
+    if (B < 1 || Hq < 1 || Hkv < 1 || Sq < 1 || Skv < 1) return set_error(QA_ERR_INVALID, "empty problem");
+    if (Hq % Hkv != 0)
+        return set_error(QA_ERR_INVALID, "Expect Hq to be a multiple of Hkv but got Hq=%d and Hkv=%d.", Hq, Hkv);
+    if (Hq > 65535 || B > 65535) return set_error(QA_ERR_INVALID, "B or Hq exceeds the grid limit 65535");
+    if (scale_mode != QA_SCALE_HEAD && scale_mode != QA_SCALE_TOKEN)
+        return set_error(QA_ERR_INVALID, "Unsupported scaling_method code: %d", scale_mode);
+    if (out_dtype != QA_DT_BF16 && out_dtype != QA_DT_FP16)
+        return set_error(QA_ERR_INVALID, "out_dtype must be bf16 or fp16");
+    if (!(sm_scale > 0.f) || !(sm_scale < 1e30f)) return set_error(QA_ERR_INVALID, "sm_scale must be positive");
+    if (p_mode == QA_P_16BIT) {
+        if (v_dtype != QA_DT_BF16 && v_dtype != QA_DT_FP16)
+            return set_error(QA_ERR_INVALID, "p_mode 16BIT needs a bf16/fp16 value tensor");
+        if (v_dtype != out_dtype) return set_error(QA_ERR_INVALID, "p_mode 16BIT: out_dtype must equal v_dtype");
+    } else if (p_mode == QA_P_E4M3 || p_mode == QA_P_E4M3_HILO) {
+        if (v_dtype != QA_DT_E4M3) return set_error(QA_ERR_INVALID, "FP8 P modes need an e4m3 value tensor");
+        if (!scale_v) return set_error(QA_ERR_INVALID, "scale_v required for an e4m3 value tensor");
+    } else {
+        return set_error(QA_ERR_INVALID, "unknown p_mode %d", p_mode);
+    }
+    if ((reinterpret_cast<uintptr_t>(q8) | reinterpret_cast<uintptr_t>(k8) | reinterpret_cast<uintptr_t>(v) |
+         reinterpret_cast<uintptr_t>(out)) & 15)
+        return set_error(QA_ERR_INVALID, "tensor base pointers must be 16-byte aligned");
+    int rc = check_device();
+    if (rc != QA_OK) return rc;
+    AttnArgs a;
+    a.q8 = q8, a.k8 = k8, a.v = v;
+    a.scale_q = scale_q, a.scale_k = scale_k, a.scale_v = scale_v;
+    a.out = out, a.lse = lse;
+    a.B = B, a.Hq = Hq, a.Hkv = Hkv, a.Sq = Sq, a.Skv = Skv, a.D = D;
+    a.causal = causal ? 1 : 0;
+    a.sm_scale = sm_scale;
+    a.scale_mode = scale_mode;
+    a.p_mode = p_mode;
+    a.v_dtype = v_dtype;
+    a.out_dtype = out_dtype;
+    return attn_fwd_dispatch(a, static_cast<cudaStream_t>(stream), &g_launches);
+}
+
+}  // extern "C"

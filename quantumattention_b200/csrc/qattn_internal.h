@@ -1,0 +1,44 @@
+// Internal declarations shared by the translation units of libqattn_sm100.so.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../include/qattn.h"
+
+namespace qa {
+
+struct QuantArgs {
+    const void* x[3];
+    void* x8[3];
+    float* scale[3];
+    int64_t strides[3][4];
+    int S[3];
+    int B, H, D;
+    float* amax_ws;
+    int rows_per_cta;
+};
+
+struct AttnArgs {
+    const void* q8;
+    const void* k8;
+    const void* v;
+    const float* scale_q;
+    const float* scale_k;
+    const float* scale_v;
+    void* out;
+    float* lse;
+    int B, Hq, Hkv, Sq, Skv, D;
+    int causal;
+    float sm_scale;
+    int scale_mode;
+    int p_mode;
+    int v_dtype;
+    int out_dtype;
+};
+
+int set_error(int code, const char* fmt, ...);
+int set_cuda_error(const char* what, cudaError_t e);
+
+int quantize_dispatch(QuantArgs& a, int x_dtype, int scale_mode, int n_tensors, cudaStream_t stream, int* launches);
+int attn_fwd_dispatch(const AttnArgs& a, cudaStream_t stream, int* launches);
+
+}  // namespace qa

@@ -1,0 +1,54 @@
+"""The C-ABI library must load without a GPU and export every symbol include/qattn.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from quantumattention_b200 import _native, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    text = open(os.path.join(ROOT, "include", "qattn.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(qa_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_builds_and_loads():
+    path = build.build_library()
+    assert os.path.exists(path)
+    lib = _native.load()
+    assert lib.qa_abi_version() == _native.ABI_VERSION
+
+
+def test_every_declared_symbol_is_exported():
+    lib = ctypes.CDLL(build.build_library())
+    declared = _declared_functions()
+    assert set(declared) == set(_native.EXPORTED_SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_argument_validation_without_gpu():
+    lib = _native.load()
+    vp = ctypes.c_void_p
+    one = (vp * 1)(16)
+    strides = (ctypes.c_int64 * 4)(1, 1, 1, 1)
+    S = (ctypes.c_int * 1)(8)
+    # bad head dim -> QA_ERR_INVALID with the reference's wording
+    rc = lib.qa_quantize_fp8(1, one, 0, strides, one, one, None, 1, 1, S, 96, 1, None)
+    assert rc == -1 and b"Unsupported head dimension: 96" in lib.qa_last_error()
+    rc = lib.qa_quantize_fp8(4, one, 0, strides, one, one, None, 1, 1, S, 64, 1, None)
+    assert rc == -1
+    rc = lib.qa_fp8_attn_fwd(16, 16, 16, 2, 16, 16, 16, 0, 16, 0, None, 1, 3, 2, 8, 8, 64, 0, 0.125, 0, None)
+    assert rc == -1 and b"multiple of Hkv" in lib.qa_last_error()
+    rc = lib.qa_fp8_attn_fwd(16, 16, 16, 0, 16, 16, None, 0, 16, 0, None, 1, 2, 2, 8, 8, 64, 0, 0.125, 0, None)
+    assert rc == -1  # fp8 P mode with a 16-bit V
+    import torch
+
+    if not torch.cuda.is_available():
+        # valid arguments but no device: must fail loudly, never fall back
+        rc = lib.qa_fp8_attn_fwd(16, 16, 16, 2, 16, 16, 16, 0, 16, 0, None, 1, 2, 2, 8, 8, 64, 0, 0.125, 0, None)
+        assert rc in (-2, -3)
