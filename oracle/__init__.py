@@ -11,6 +11,6 @@ fp32 inputs, and the attention restatement against ``quantum_attn.ops._fp8_atten
 """
 from .e4m3 import E4M3_MAX, decode_table, e4m3_decode, e4m3_encode_rne_sat  # noqa: F401
 from .quantize_ref import dequantize, quantize_fp8  # noqa: F401
-from .attention_ref import attention_flops, fp8_attention_ref, sdpa_ref  # noqa: F401
+from .attention_ref import attention_flops, cpu_reference_step, fp8_attention_ref, sdpa_ref  # noqa: F401
 from .metrics import compare  # noqa: F401
 from .inputs import CONFIGS, make_qkv  # noqa: F401

@@ -63,3 +63,18 @@ def attention_flops(B, H, Sq, Skv, D, causal):
     """Algorithmic FLOPs, the reference's own formula (tests/test_interface.py:121-125)."""
     f = 4 * B * H * Sq * Skv * D
     return f // 2 if causal else f
+
+
+def cpu_reference_step(q8, k8, v, scale_q, scale_k, *, is_causal=False, scale=None):
+    """The reference's op definition executed on the host cores (the CPU arm of bench.py).
+
+    Follows src/quantum_attn/ops.py:64-95 literally - cast q8/k8 up, multiply by the scales, aten SDPA - but in fp32
+    and with the MATH backend, which is the arithmetic BASELINE.json names for the CPU baseline.  Inputs are torch
+    CPU tensors: q8/k8 float8_e4m3fn, v fp32, scales fp32 ([B,H]).
+    """
+    from torch.nn.attention import SDPBackend, sdpa_kernel
+
+    q = q8.to(torch.float32) * scale_q[..., None, None]
+    k = k8.to(torch.float32) * scale_k[..., None, None]
+    with sdpa_kernel(SDPBackend.MATH):
+        return torch.nn.functional.scaled_dot_product_attention(q, k, v, is_causal=is_causal, scale=scale)

@@ -30,6 +30,11 @@ EXPORTED_SYMBOLS = (
 _lib = None
 _lock = threading.Lock()
 
+# bookkeeping for bench.py: kernels launched through this binding, and an optional CUDA-event timer around the
+# attention kernel (events are recorded on the launching stream; a few hundred ns each)
+launch_total = 0
+attn_events = None  # set to a list to collect (start_event, stop_event) pairs
+
 
 class NativeError(RuntimeError):
     pass
@@ -135,6 +140,8 @@ def quantize_fp8(tensors: Sequence[torch.Tensor], scale_mode: int) -> Tuple[list
         rc = lib.qa_quantize_fp8(n, x_arr, _dt_code(t0.dtype), strides, o_arr, s_arr, ws_ptr, B, H, S, D,
                                  scale_mode, stream)
     _check(rc, "qa_quantize_fp8")
+    global launch_total
+    launch_total += int(lib.qa_last_launch_count())
     return outs, scales
 
 
@@ -154,12 +161,21 @@ def fp8_attn_fwd(q8: torch.Tensor, k8: torch.Tensor, v: torch.Tensor, scale_q: t
     out = torch.empty((B, Hq, Sq, D), dtype=out_dtype, device=dev)
     lse = torch.empty((B, Hq, Sq), dtype=torch.float32, device=dev) if return_lse else None
     with torch.cuda.device(dev):
-        stream = torch.cuda.current_stream(dev).cuda_stream
+        tstream = torch.cuda.current_stream(dev)
+        stream = tstream.cuda_stream
+        if attn_events is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(tstream)
         rc = lib.qa_fp8_attn_fwd(
             q8.data_ptr(), k8.data_ptr(), v.data_ptr(), _dt_code(v.dtype), scale_q.data_ptr(), scale_k.data_ptr(),
             scale_v.data_ptr() if scale_v is not None else None, scale_mode, out.data_ptr(), _dt_code(out_dtype),
             lse.data_ptr() if lse is not None else None, B, Hq, Hkv, Sq, Skv, D, int(bool(is_causal)),
             float(sm_scale), p_mode, stream,
         )
+        if attn_events is not None:
+            ev1.record(tstream)
+            attn_events.append((ev0, ev1))
     _check(rc, "qa_fp8_attn_fwd")
+    global launch_total
+    launch_total += int(lib.qa_last_launch_count())
     return (out, lse) if return_lse else out

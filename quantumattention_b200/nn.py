@@ -13,6 +13,7 @@ SURVEY.md Appendix B).
 from __future__ import annotations
 
 import functools
+import math
 from typing import Optional, Tuple
 
 import torch
@@ -195,6 +196,33 @@ def _fp8_attention_wrapper(query, key, value, attn_mask=None, dropout_p=0.0, is_
     )
 
 
+def _fp8_attention_direct(query, key, value, is_causal, scale, scale_q, scale_k, scaling_method):
+    """Eager hot path: no dispatcher hop - quantise everything that needs it in ONE launch pair, then the kernel.
+
+    Launch sequence for 16-bit q, k, v in "fp8" mode: memset, amax(q,k,v), quantise(q,k,v), attention.
+    """
+    mode = _native.QA_SCALE_HEAD if scaling_method == "head-wise" else _native.QA_SCALE_TOKEN
+    p_mode = ops.pv_mode_code()
+    v_fp8 = p_mode != _native.QA_P_16BIT
+    scale_v = None
+    out_dtype = value.dtype if value.dtype in (torch.float16, torch.bfloat16) else torch.bfloat16
+    if scale_q is None:
+        same_heads = query.shape[1] == key.shape[1]
+        if v_fp8 and same_heads and mode == _native.QA_SCALE_HEAD and value.dtype == query.dtype:
+            (query, key, value), (scale_q, scale_k, scale_v) = _native.quantize_fp8([query, key, value], mode)
+        elif same_heads:
+            (query, key), (scale_q, scale_k) = _native.quantize_fp8([query, key], mode)
+        else:
+            (query,), (scale_q,) = _native.quantize_fp8([query], mode)
+            (key,), (scale_k,) = _native.quantize_fp8([key], mode)
+    if v_fp8 and scale_v is None:
+        (value,), (scale_v,) = _native.quantize_fp8([value], _native.QA_SCALE_HEAD)
+
+    sm_scale = (1.0 / math.sqrt(query.size(-1))) if scale is None else float(scale)
+    return _native.fp8_attn_fwd(query, key, value, scale_q, scale_k, scale_v, scale_mode=mode, is_causal=is_causal,
+                                sm_scale=sm_scale, p_mode=p_mode, out_dtype=out_dtype)
+
+
 def fp8_attention(query, key, value, attn_mask=None, dropout_p=0.0, is_causal=False, *, scale=None, scale_q=None,
                   scale_k=None, scaling_method=None) -> torch.Tensor:
     supported, reason = can_use_attention(
@@ -203,6 +231,14 @@ def fp8_attention(query, key, value, attn_mask=None, dropout_p=0.0, is_causal=Fa
     )
     if not supported:
         raise ValueError(reason)
+    from torch._subclasses.fake_tensor import is_fake
+
+    traced = torch.compiler.is_dynamo_compiling() or any(
+        is_fake(x) for x in (query, key, value, scale_q, scale_k) if x is not None)
+    if not traced and not config.attention.force_eager_fallback:
+        if (scale_q is None) != (scale_k is None):
+            raise ValueError("scale_q and scale_k must be both provided or both not provided")
+        return _fp8_attention_direct(query, key, value, is_causal, scale, scale_q, scale_k, scaling_method)
     return _fp8_attention_wrapper(
         query, key, value, attn_mask=attn_mask, dropout_p=dropout_p, is_causal=is_causal, scale=scale,
         scale_q=scale_q, scale_k=scale_k, scaling_method=scaling_method,
