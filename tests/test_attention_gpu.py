@@ -233,7 +233,8 @@ def test_full_size_properties(name):
                 perm = torch.randperm(S, generator=torch.Generator().manual_seed(1)).cuda()
                 outp = quantum_attn.fp8_attn_func(qc, kc[:, :, perm], vc[:, :, perm], is_causal=False)
                 m = oracle.compare(outp.float().cpu().numpy(), out.float().cpu().numpy())
-                assert m["cos_sim"] > 0.9995, m
+                # two runs that round P to e4m3 in different key orders differ by ~sqrt(2) x the single-run error
+                assert m["cos_sim"] > (0.999 if pv == "fp8" else 0.99995), m
         # oracle on a slice: 2 heads x 3 row blocks (first, middle, last rows)
         (q8, k8), (sq, sk) = _native.quantize_fp8([qc, kc], _native.QA_SCALE_HEAD)
         heads = [0, H - 1]
