@@ -41,7 +41,8 @@ class NativeError(RuntimeError):
 
 
 def lib_path() -> str:
-    return _build.LIB_PATH
+    # QA_NATIVE_LIB: developer override to A/B kernel variants built by scripts/build_variant.sh
+    return os.environ.get("QA_NATIVE_LIB") or _build.LIB_PATH
 
 
 def load(build_if_missing: bool = True):

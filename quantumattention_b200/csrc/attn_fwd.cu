@@ -6,13 +6,18 @@
 // (:355-647).  Same function (dequant scale folded into the exp2 argument as in :204-210,248-250; top-left causal
 // mask as in :252-263; ragged tails via TMA zero fill + -inf columns as in :269-271), different machine:
 //
-//   CTA = 2 query tiles of 128 rows (ping-pong), 12 warps (3 warpgroups; setmaxnreg moves registers to softmax):
-//     warps 0-3  softmax + correction + epilogue of query tile 0      (thread r <-> TMEM lane r <-> query row r)
+//   CTA = 2 query tiles of 128 rows, 12 warps (3 warpgroups; setmaxnreg moves registers to the softmax warps):
+//     warps 0-3  softmax + (rare) O rescale + epilogue of query tile 0   (thread r <-> TMEM lane r <-> query row r)
 //     warps 4-7  the same for query tile 1
-//     warp  8    MMA issuer (one thread): QK_0, QK_1, PV_0, PV_1 interleaved so one tile's softmax hides behind
-//                the other tile's MMAs
-//     warp  9    TMA producer: Q once, K/V tiles through an mbarrier ring        (warps 10-11 idle)
-//   TMEM (512 columns): S0 | S1 | O0 | O1, 128 columns each at D=128; P_t aliases the first columns of S_t.
+//     warp  8    MMA issuer (one thread)
+//     warp  9    TMA producer: Q once, K/V tiles of 128 keys through mbarrier rings      (warps 10-11 idle)
+//   The softmax / MMA hand-off runs in STEPS of 64 keys, and every query tile owns TWO score buffers in TMEM:
+//   while the softmax warps work on S_j the tensor core already holds S_{j+1}, and QK_{j+2} / PV_j are issued
+//   the moment P_j lands.  The softmax chain never waits for an MMA in steady state, which matters because at
+//   D = 128 the exp unit (MUFU, 16 / clk / SM), not the tensor pipe, is the tighter bound of FP8 attention.
+//   To go past that bound a compile-time fraction of the exponentials is evaluated on the FMA pipe
+//   (Cody-Waite split + minimax polynomial, packed fp32x2 arithmetic) instead of MUFU.EX2.
+//   TMEM (512 columns): S(t,b) at t*128 + b*64 | O_t at 256 + t*128; P_j aliases the first columns of its S buffer.
 //   K and V tiles are shared by both query tiles, halving L2->SMEM traffic per FLOP.
 //
 // Deliberately absent: any non-sm_100 path, any fallback.
@@ -26,8 +31,13 @@
 namespace qa {
 
 constexpr int BM = 128;  // query rows per tile (= TMEM lanes)
-constexpr int BN = 128;  // keys per K/V tile
+constexpr int BN = 128;  // keys per K/V shared-memory tile (one TMA box)
+constexpr int BS = 64;   // keys per softmax / MMA step (half a tile)
 constexpr float kLog2e = 1.4426950408889634f;
+
+#ifndef QA_POLY_NUM
+#define QA_POLY_NUM 2  // of every 8 pairs of exponentials, how many run on the FMA pipe instead of MUFU
+#endif
 
 template <int D_, int PMODE_>
 struct AttnCfg {
@@ -61,13 +71,15 @@ struct AttnCfg {
     static_assert(SMEM_TOTAL <= 232448, "shared memory budget exceeded");
     static constexpr int NTHREADS = (NQ * 4 + 4) * 32;  // softmax warpgroups + one warpgroup holding the MMA / TMA warps
     // TMEM columns
-    static constexpr int TM_S = 0;                        // S_t at t * 128
+    static constexpr int TM_S = 0;                        // S(t, b) at t * 128 + b * 64
     static constexpr int TM_O = 256;                      // O_t at 256 + t * 128 (D <= 128), single O at D = 256
-    static constexpr int P_COLS = V16 ? 64 : 32;          // columns holding one P tile
-    static constexpr int TM_P_LO = 64;                    // hi/lo mode: second P tile at S_t + 64
+    static constexpr int TM_P_LO = 16;                    // hi/lo mode: second P tile 16 columns after the first
     // softmax range management: p' = 2^KOFF * exp2(s - m_used), m_used may lag the true max by <= TAU (log2 units)
     static constexpr float KOFF = V16 ? 0.f : 4.f;
     static constexpr float TAU = V16 ? 8.f : 4.f;
+    // exponentials on the FMA pipe: polynomial degree (a single e4m3 P tolerates the quadratic's 1.7e-3)
+    static constexpr int POLY_NUM = QA_POLY_NUM;
+    static constexpr int POLY_DEG = (PMODE_ == QA_P_E4M3) ? 2 : 3;
 };
 
 struct AttnParams {
@@ -85,7 +97,8 @@ struct AttnParams {
 struct Barriers {
     uint64_t q_full[2];
     uint64_t k_full[4], k_empty[4], v_full[4], v_empty[4];
-    uint64_t s_full[2], p_full[2], o_full[2];
+    uint64_t s_full[2][2], p_full[2][2];  // [tile][score buffer]
+    uint64_t pv_done[2], o_full[2];
     uint32_t tmem_base;
 };
 static_assert(sizeof(Barriers) <= 256, "barrier block too large");
@@ -94,6 +107,39 @@ template <class C>
 __device__ __forceinline__ uint32_t qk_koff(int k) {  // byte offset of the k-th 32-byte K slice inside a Q/K tile
     constexpr int per_box = C::QK_ROW / 32;
     return uint32_t(k / per_box) * C::QK_BOX_BYTES + uint32_t(k % per_box) * 32u;
+}
+
+// ------------------------------------------------------------------------------------------------ exp2 helpers
+// 2^x for a pair of arguments on the FMA / ALU pipes: x = n + f with n = round(x) taken from the low mantissa bits of
+// x + 1.5 * 2^23, f in [-0.5, 0.5], 2^f by a minimax polynomial (relative error 1.7e-3 / 7.5e-5 for degree 2 / 3),
+// and n added straight into the exponent field.  Arguments are clamped at -125 (result ~ 2^-125, i.e. zero).
+template <int DEG>
+__device__ __forceinline__ float2 exp2_poly(float2 x) {
+    x.x = fmaxf(x.x, -125.f);
+    x.y = fmaxf(x.y, -125.f);
+    const float2 magic = make_float2(12582912.f, 12582912.f);
+    const float2 t = __fadd2_rn(x, magic);
+    const float2 n = __fadd2_rn(t, make_float2(-12582912.f, -12582912.f));
+    const float2 f = __ffma2_rn(n, make_float2(-1.f, -1.f), x);
+    float2 q;
+    if constexpr (DEG == 2) {
+        q = __ffma2_rn(f, make_float2(0.23842893540859222f, 0.23842893540859222f),
+                       make_float2(0.7034479975700378f, 0.7034479975700378f));
+        q = __ffma2_rn(q, f, make_float2(1.0004431009292603f, 1.0004431009292603f));
+    } else {
+        q = __ffma2_rn(f, make_float2(0.0551716685295105f, 0.0551716685295105f),
+                       make_float2(0.2426111251115799f, 0.2426111251115799f));
+        q = __ffma2_rn(q, f, make_float2(0.6932609677314758f, 0.6932609677314758f));
+        q = __ffma2_rn(q, f, make_float2(0.9999280571937561f, 0.9999280571937561f));
+    }
+    float2 r;
+    r.x = __int_as_float(__float_as_int(q.x) + (__float_as_int(t.x) << 23));
+    r.y = __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23));
+    return r;
+}
+
+__host__ __device__ constexpr bool pair_uses_poly(int i, int num) {  // spread `num` of every 8 pairs evenly
+    return (((i & 7) + 1) * num) / 8 > ((i & 7) * num) / 8;
 }
 
 template <class C, bool CAUSAL, bool TOKEN>
@@ -115,12 +161,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // heavy (late) causal query blocks are scheduled first
     const int mblk = CAUSAL ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
     const int m0 = mblk * (BM * NQ);
-    const int nkv = (p.Skv + BN - 1) / BN;
-    // per-tile trip counts: under a causal mask tile t only needs K/V tiles up to its own diagonal
-    const int n_iter0 = CAUSAL ? min(nkv, m0 / BN + 1) : nkv;
-    const int n_iter1 = CAUSAL ? min(nkv, (m0 + BM) / BN + 1) : nkv;
-    auto n_iter = [&](int t) { return t == 0 ? n_iter0 : n_iter1; };
-    const int n_max = n_iter(NQ - 1);
+    const int nst_all = (p.Skv + BS - 1) / BS;
+    // per-tile trip counts in 64-key steps: under a causal mask tile t stops at its own diagonal
+    const int nst0 = CAUSAL ? min(nst_all, m0 / BS + 2) : nst_all;
+    const int nst1 = CAUSAL ? min(nst_all, (m0 + BM) / BS + 2) : nst_all;
+    auto n_steps = [&](int t) { return t == 0 ? nst0 : nst1; };
+    const int n_max = n_steps(NQ - 1);
+    const int n_kv = (n_max + 1) >> 1;  // K/V tiles of 128 keys
 
     // ------------------------------------------------------------------ one-time setup
     if (warp == 0) {
@@ -130,9 +177,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     if (threadIdx.x == 32) {
         for (int t = 0; t < 2; ++t) {
             mbar_init(&bars->q_full[t], 1);
-            mbar_init(&bars->s_full[t], 1);
-            mbar_init(&bars->p_full[t], 128);
+            mbar_init(&bars->pv_done[t], 1);
             mbar_init(&bars->o_full[t], 1);
+            for (int bb = 0; bb < 2; ++bb) {
+                mbar_init(&bars->s_full[t][bb], 1);
+                mbar_init(&bars->p_full[t][bb], 128);
+            }
         }
         for (int s = 0; s < 4; ++s) {
             mbar_init(&bars->k_full[s], 1);
@@ -151,125 +201,154 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = bars->tmem_base;
+    if (bars->tmem_base != 0) __trap();  // the CTA owns all 512 columns, so the allocation starts at column 0
+    constexpr uint32_t tmem = 0;
 
     // register rebalancing (two-tile configs run 384 threads -> 168 registers each at launch): the softmax
-    // warpgroups keep a whole 128-wide score row per thread in registers, the MMA / TMA warps need almost nothing
+    // warpgroups keep a whole score row per thread in registers, the MMA / TMA warps need almost nothing
     if (warp >= NQ * 4) {
         if constexpr (NQ == 2) reg_dealloc<56>();
         if (warp == NQ * 4 + 1) {
-        // =============================================================== TMA producer
-        if (lane == 0) {
-            for (int t = 0; t < NQ; ++t) {
-                mbar_arrive_expect_tx(&bars->q_full[t], C::Q_TILE);
-                for (int x = 0; x < C::QK_BOXES; ++x)
-                    tma_load_3d(smem + C::SMEM_Q + t * C::Q_TILE + x * C::QK_BOX_BYTES, &tmQ, &bars->q_full[t],
-                                x * C::QK_ROW, m0 + t * BM, bh, kEvictFirst);
+            // =========================================================== TMA producer
+            if (lane == 0) {
+                for (int t = 0; t < NQ; ++t) {
+                    mbar_arrive_expect_tx(&bars->q_full[t], C::Q_TILE);
+                    for (int x = 0; x < C::QK_BOXES; ++x)
+                        tma_load_3d(smem + C::SMEM_Q + t * C::Q_TILE + x * C::QK_BOX_BYTES, &tmQ, &bars->q_full[t],
+                                    x * C::QK_ROW, m0 + t * BM, bh, kEvictFirst);
+                }
+                for (int n = 0; n < n_kv; ++n) {
+                    const int s = n % C::STAGES;
+                    const uint32_t ph = (n / C::STAGES) & 1;
+                    mbar_wait(&bars->k_empty[s], ph ^ 1);
+                    mbar_arrive_expect_tx(&bars->k_full[s], C::K_TILE);
+                    for (int x = 0; x < C::QK_BOXES; ++x)
+                        tma_load_3d(smem + C::SMEM_K + s * C::K_TILE + x * C::QK_BOX_BYTES, &tmK, &bars->k_full[s],
+                                    x * C::QK_ROW, n * BN, bhkv, kEvictLast);
+                    mbar_wait(&bars->v_empty[s], ph ^ 1);
+                    mbar_arrive_expect_tx(&bars->v_full[s], C::V_TILE);
+                    for (int x = 0; x < C::V_BOXES; ++x)
+                        tma_load_3d(smem + C::SMEM_V + s * C::V_TILE + x * C::V_BOX_BYTES, &tmV, &bars->v_full[s],
+                                    x * (C::V_ROW / C::VB), n * BN, bhkv, kEvictLast);
+                }
             }
-            for (int n = 0; n < n_max; ++n) {
-                const int s = n % C::STAGES;
-                const uint32_t ph = (n / C::STAGES) & 1;
-                mbar_wait(&bars->k_empty[s], ph ^ 1);
-                mbar_arrive_expect_tx(&bars->k_full[s], C::K_TILE);
-                for (int x = 0; x < C::QK_BOXES; ++x)
-                    tma_load_3d(smem + C::SMEM_K + s * C::K_TILE + x * C::QK_BOX_BYTES, &tmK, &bars->k_full[s],
-                                x * C::QK_ROW, n * BN, bhkv, kEvictLast);
-                mbar_wait(&bars->v_empty[s], ph ^ 1);
-                mbar_arrive_expect_tx(&bars->v_full[s], C::V_TILE);
-                for (int x = 0; x < C::V_BOXES; ++x)
-                    tma_load_3d(smem + C::SMEM_V + s * C::V_TILE + x * C::V_BOX_BYTES, &tmV, &bars->v_full[s],
-                                x * (C::V_ROW / C::VB), n * BN, bhkv, kEvictLast);
-            }
-        }
-    } else if (warp == NQ * 4) {
-        // =============================================================== MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc_qk = make_idesc(0, 0, 0, 0, BM, BN);
-            constexpr uint32_t idesc_pv = C::V16 ? 0u : make_idesc(0, 0, 0, 1, BM, D);
-            const uint32_t idesc_pv16 = make_idesc(p.out_fp16 ? 0 : 1, p.out_fp16 ? 0 : 1, 0, 1, BM, D);
+        } else if (warp == NQ * 4) {
+            // =========================================================== MMA issuer
+            // The whole warp walks the loop converged (so addresses and descriptors stay on the uniform datapath);
+            // one elected lane issues the tcgen05 instructions.  Descriptors are built once: per MMA only the
+            // 14-bit start-address field of the low word changes.
+            constexpr uint32_t idesc_qk = make_idesc(0, 0, 0, 0, BM, BS);
+            constexpr uint32_t idesc_pv8 = make_idesc(0, 0, 0, 1, BM, D);
+            const uint32_t idesc_pv = C::V16 ? make_idesc(p.out_fp16 ? 0 : 1, p.out_fp16 ? 0 : 1, 0, 1, BM, D) : idesc_pv8;
             constexpr uint64_t qk_swz = (C::QK_ROW == 128) ? kSwz128 : kSwz64;
             constexpr uint64_t v_swz = (C::V_ROW == 128) ? kSwz128 : kSwz64;
-            const uint32_t q_base = smem_u32(smem + C::SMEM_Q);
-            const uint32_t k_base = smem_u32(smem + C::SMEM_K);
-            const uint32_t v_base = smem_u32(smem + C::SMEM_V);
+            const uint64_t q_desc0 = make_smem_desc(smem_u32(smem + C::SMEM_Q), 16, 8 * C::QK_ROW, qk_swz);
+            const uint64_t k_desc0 = make_smem_desc(smem_u32(smem + C::SMEM_K), 16, 8 * C::QK_ROW, qk_swz);
+            const uint64_t v_desc0 = make_smem_desc(smem_u32(smem + C::SMEM_V), C::V_BOX_BYTES, 8 * C::V_ROW, v_swz);
+            constexpr int KEYS_PER_PV = C::V16 ? 16 : 32;
 
-            auto issue_qk = [&](int t, int stage) {
+            // S(t, j & 1) = Q_t . K[keys of step j]^T : 64 key rows starting at (j & 1) * 64 of the K tile
+            auto issue_qk = [&](int t, int stage, int j) {
+                const uint32_t s_t = C::TM_S + t * 128 + (j & 1) * BS;
+                const uint64_t ad = q_desc0 + uint64_t((t * C::Q_TILE) >> 4);
+                const uint64_t bd = k_desc0 + uint64_t((stage * C::K_TILE + (j & 1) * (BS * C::QK_ROW)) >> 4);
 #pragma unroll
-                for (int k = 0; k < D / 32; ++k) {
-                    uint64_t ad = make_smem_desc(q_base + t * C::Q_TILE + qk_koff<C>(k), 16, 8 * C::QK_ROW, qk_swz);
-                    uint64_t bd = make_smem_desc(k_base + stage * C::K_TILE + qk_koff<C>(k), 16, 8 * C::QK_ROW, qk_swz);
-                    umma_f8_ss(tmem + C::TM_S + t * 128, ad, bd, idesc_qk, k > 0);
-                }
+                for (int k = 0; k < D / 32; ++k)
+                    umma_f8_ss(s_t, ad + (qk_koff<C>(k) >> 4), bd + (qk_koff<C>(k) >> 4), idesc_qk, k > 0);
             };
-            auto issue_pv = [&](int t, int stage, bool acc) {
-                const uint32_t o_t = tmem + C::TM_O + (NQ == 2 ? t * 128 : 0);
-                const uint32_t p_t = tmem + C::TM_S + t * 128;
-                if constexpr (!C::V16) {
+            // O_t (+)= P_j . V[keys of step j]
+            auto issue_pv = [&](int t, int stage, int j, bool acc) {
+                const uint32_t o_t = C::TM_O + (NQ == 2 ? t * 128 : 0);
+                const uint32_t p_t = C::TM_S + t * 128 + (j & 1) * BS;
+                const uint64_t bd = v_desc0 + uint64_t((stage * C::V_TILE + (j & 1) * (BS * C::V_ROW)) >> 4);
 #pragma unroll
-                    for (int k = 0; k < BN / 32; ++k) {  // 32 keys per instruction
-                        uint64_t bd = make_smem_desc(v_base + stage * C::V_TILE + k * 32 * C::V_ROW, C::V_BOX_BYTES,
-                                                     8 * C::V_ROW, v_swz);
-                        umma_f8_ts(o_t, p_t + k * 8, bd, idesc_pv, (acc || k > 0) ? 1u : 0u);
-                        if constexpr (C::PMODE == QA_P_E4M3_HILO)
-                            umma_f8_ts(o_t, p_t + C::TM_P_LO + k * 8, bd, idesc_pv, 1u);
-                    }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < BN / 16; ++k) {  // 16 keys per instruction
-                        uint64_t bd = make_smem_desc(v_base + stage * C::V_TILE + k * 16 * C::V_ROW, C::V_BOX_BYTES,
-                                                     8 * C::V_ROW, v_swz);
-                        umma_f16_ts(o_t, p_t + k * 8, bd, idesc_pv16, (acc || k > 0) ? 1u : 0u);
+                for (int k = 0; k < BS / KEYS_PER_PV; ++k) {
+                    const uint64_t bk = bd + uint64_t((k * KEYS_PER_PV * C::V_ROW) >> 4);
+                    if constexpr (!C::V16) {
+                        umma_f8_ts(o_t, p_t + k * 8, bk, idesc_pv, (acc || k > 0) ? 1u : 0u);
+                        if constexpr (C::PMODE == QA_P_E4M3_HILO) umma_f8_ts(o_t, p_t + C::TM_P_LO + k * 8, bk, idesc_pv, 1u);
+                    } else {
+                        umma_f16_ts(o_t, p_t + k * 8, bk, idesc_pv, (acc || k > 0) ? 1u : 0u);
                     }
                 }
             };
 
-            // prologue: S_t = Q_t K_0^T
+            // prologue: the first two score buffers of every tile come from K tile 0
             mbar_wait(&bars->k_full[0], 0);
             for (int t = 0; t < NQ; ++t) {
                 mbar_wait(&bars->q_full[t], 0);
                 tc_fence_after();
-                issue_qk(t, 0);
-                umma_commit(&bars->s_full[t]);
+                if (elect_one()) {
+                    issue_qk(t, 0, 0);
+                    umma_commit(&bars->s_full[t][0]);
+                }
+                __syncwarp();
             }
-            umma_commit(&bars->k_empty[0]);
+            for (int t = 0; t < NQ; ++t) {
+                if (1 < n_steps(t)) {
+                    if (elect_one()) {
+                        issue_qk(t, 0, 1);
+                        umma_commit(&bars->s_full[t][1]);
+                    }
+                    __syncwarp();
+                }
+            }
+            if (elect_one()) umma_commit(&bars->k_empty[0]);
+            __syncwarp();
 
-            for (int n = 0; n < n_max; ++n) {
-                const int sv = n % C::STAGES;
-                const int sk = (n + 1) % C::STAGES;
-                const uint32_t ph_v = (n / C::STAGES) & 1;
-                const uint32_t ph_k = ((n + 1) / C::STAGES) & 1;
-                mbar_wait(&bars->v_full[sv], ph_v);
-                bool k_ready = false;
+            for (int j = 0; j < n_max; ++j) {
+                const int kt = j >> 1;
+                const int sv = kt % C::STAGES;
+                if ((j & 1) == 0) {
+                    mbar_wait(&bars->v_full[sv], (kt / C::STAGES) & 1);
+                    tc_fence_after();
+                }
+                const int jn = j + 2;
+                const int ktn = jn >> 1;
+                const int skn = ktn % C::STAGES;
+                bool k_ready = (jn & 1) != 0;  // the odd step's K tile was waited for one iteration earlier
 #pragma unroll
                 for (int t = 0; t < NQ; ++t) {
-                    if (n < n_iter(t)) {
-                        mbar_wait(&bars->p_full[t], n & 1);
+                    if (j < n_steps(t)) {
+                        mbar_wait(&bars->p_full[t][j & 1], (j >> 1) & 1);
                         tc_fence_after();
-                        issue_pv(t, sv, n > 0);
+                        if (elect_one()) {
+                            issue_pv(t, sv, j, j > 0);
+                            umma_commit(&bars->pv_done[t]);
+                        }
+                        __syncwarp();
                     }
-                    if (t == NQ - 1) umma_commit(&bars->v_empty[sv]);
-                    if (n + 1 < n_iter(t)) {
+                    if (jn < n_steps(t)) {
                         if (!k_ready) {
-                            mbar_wait(&bars->k_full[sk], ph_k);
+                            mbar_wait(&bars->k_full[skn], (ktn / C::STAGES) & 1);
                             tc_fence_after();
                             k_ready = true;
                         }
-                        issue_qk(t, sk);
-                        umma_commit(&bars->s_full[t]);
+                        if (elect_one()) {
+                            issue_qk(t, skn, jn);
+                            umma_commit(&bars->s_full[t][jn & 1]);
+                        }
+                        __syncwarp();
                     }
-                    if (t == NQ - 1 && n + 1 < n_max) umma_commit(&bars->k_empty[sk]);
                 }
+                if (elect_one()) {
+                    if ((j & 1) == 1 || j == n_max - 1) umma_commit(&bars->v_empty[sv]);
+                    if (jn < n_max && ((jn & 1) == 1 || jn == n_max - 1)) umma_commit(&bars->k_empty[skn]);
+                }
+                __syncwarp();
             }
-            for (int t = 0; t < NQ; ++t) umma_commit(&bars->o_full[t]);
+            if (elect_one()) {
+                for (int t = 0; t < NQ; ++t) umma_commit(&bars->o_full[t]);
+            }
+            __syncwarp();
         }
-    }
     } else {
         // =============================================================== softmax / correction / epilogue
         if constexpr (NQ == 2) reg_alloc<224>();
         const int t = warp >> 2;                       // query tile of this warpgroup
         const int row = ((warp & 3) << 5) | lane;      // row inside the tile == TMEM lane
         const uint32_t lane_base = uint32_t((warp & 3) * 32) << 16;
-        const uint32_t s_addr = tmem + lane_base + C::TM_S + t * 128;
+        const uint32_t s_base = tmem + lane_base + C::TM_S + t * 128;
         const uint32_t o_addr = tmem + lane_base + C::TM_O + (NQ == 2 ? t * 128 : 0);
         const int row_g = m0 + t * BM + row;
 
@@ -280,117 +359,120 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             c = p.scale_q[bh] * p.scale_k[bhkv] * p.sm_scale_log2;
         }
         const float* sk_row = TOKEN ? p.scale_k + size_t(bhkv) * p.Skv : nullptr;
+        const float2 c2 = make_float2(c, c);
 
         float m_used = -INFINITY;  // running max in raw score units (times per-column scale in token mode)
-        float l = 0.f;             // running sum of p' = 2^KOFF * exp2(c * (s - m_used))
-        const int my_iters = n_iter(t);
+        float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);  // running sum of p' (4 partial sums)
+        const int my_steps = n_steps(t);
 
-        for (int n = 0; n < my_iters; ++n) {
-            mbar_wait(&bars->s_full[t], n & 1);
+        for (int j = 0; j < my_steps; ++j) {
+            const uint32_t s_addr = s_base + (j & 1) * BS;
+            mbar_wait(&bars->s_full[t][j & 1], (j >> 1) & 1);
             tc_fence_after();
-            float s[128];
-            tmem_ld_x32(s_addr + 0, &s[0]);
-            tmem_ld_x32(s_addr + 32, &s[32]);
-            tmem_ld_x32(s_addr + 64, &s[64]);
-            tmem_ld_x32(s_addr + 96, &s[96]);
+            float s[BS];
+            tmem_ld_f64(s_addr, s);
             tmem_ld_wait();
-            const int col0 = n * BN;
+            const int col0 = j * BS;
             if constexpr (TOKEN) {
-                if (col0 + BN <= p.Skv) {
+                if (col0 + BS <= p.Skv && (p.Skv & 3) == 0) {  // rows of scale_k stay 16-byte aligned
 #pragma unroll
-                    for (int j = 0; j < 128; j += 4) {
-                        float4 k4 = __ldg(reinterpret_cast<const float4*>(sk_row + col0 + j));
-                        s[j] *= k4.x, s[j + 1] *= k4.y, s[j + 2] *= k4.z, s[j + 3] *= k4.w;
+                    for (int i = 0; i < BS; i += 4) {
+                        float4 k4 = __ldg(reinterpret_cast<const float4*>(sk_row + col0 + i));
+                        s[i] *= k4.x, s[i + 1] *= k4.y, s[i + 2] *= k4.z, s[i + 3] *= k4.w;
                     }
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 128; ++j) s[j] *= __ldg(sk_row + min(col0 + j, p.Skv - 1));
+                    for (int i = 0; i < BS; ++i) s[i] *= __ldg(sk_row + min(col0 + i, p.Skv - 1));
                 }
             }
-            // masking: only tiles that touch the causal diagonal or the ragged tail pay for it
-            const bool tail = col0 + BN > p.Skv;
-            const bool diag = CAUSAL && (col0 + BN - 1 > m0 + t * BM);
+            // masking: only steps that touch the causal diagonal or the ragged tail pay for it
+            const bool tail = col0 + BS > p.Skv;
+            const bool diag = CAUSAL && (col0 + BS - 1 > m0 + t * BM);
             if (tail || diag) {
                 const int lim = CAUSAL ? min(p.Skv - 1, row_g) : (p.Skv - 1);  // last visible column
 #pragma unroll
-                for (int j = 0; j < 128; ++j)
-                    if (col0 + j > lim) s[j] = -INFINITY;
+                for (int i = 0; i < BS; ++i)
+                    if (col0 + i > lim) s[i] = -INFINITY;
             }
             float mx0 = fmaxf(s[0], s[1]), mx1 = fmaxf(s[2], s[3]);
 #pragma unroll
-            for (int j = 4; j < 128; j += 4) {
-                mx0 = fmaxf(mx0, fmaxf(s[j], s[j + 1]));
-                mx1 = fmaxf(mx1, fmaxf(s[j + 2], s[j + 3]));
+            for (int i = 4; i < BS; i += 4) {
+                mx0 = fmaxf(mx0, fmaxf(s[i], s[i + 1]));
+                mx1 = fmaxf(mx1, fmaxf(s[i + 2], s[i + 3]));
             }
             const float m_new = fmaxf(m_used, fmaxf(mx0, mx1));
             // lazy rescale: keep the stale max while the true max has grown by < 2^TAU
             const bool grow = (m_new - m_used) * c > C::TAU;
             if (__any_sync(0xffffffffu, grow)) {
-                const float alpha = ex2_approx((m_used - m_new) * c);  // 0 on the first tile
+                const float alpha = ex2_approx((m_used - m_new) * c);  // 0 on the first step
                 m_used = m_new;
-                l *= alpha;
-                if (n > 0) {
+                la.x *= alpha, la.y *= alpha, lb.x *= alpha, lb.y *= alpha;
+                if (j > 0) {
+                    // O_t must be quiescent: PV_{j-1} is the only MMA that can still be writing it
+                    mbar_wait(&bars->pv_done[t], (j - 1) & 1);
+                    tc_fence_after();
 #pragma unroll
                     for (int cc = 0; cc < D; cc += 32) {
                         float o[32];
                         tmem_ld_x32(o_addr + cc, o);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) o[j] *= alpha;
+                        for (int i = 0; i < 32; ++i) o[i] *= alpha;
                         tmem_st_x32(o_addr + cc, o);
                     }
                 }
             }
             const float neg = C::KOFF - m_used * c;
-            float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+            const float2 neg2 = make_float2(neg, neg);
+
+            // p' for one pair of columns; a compile-time subset of the pairs avoids MUFU
+            auto exp_pair = [&](int i) -> float2 {
+                const float2 x = __ffma2_rn(make_float2(s[2 * i], s[2 * i + 1]), c2, neg2);
+                if (pair_uses_poly(i, C::POLY_NUM)) return exp2_poly<C::POLY_DEG>(x);
+                return make_float2(ex2_approx(x.x), ex2_approx(x.y));
+            };
+
             if constexpr (C::PMODE == QA_P_E4M3) {
-                uint32_t pw[32];
+                uint32_t pw[BS / 4];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float p0 = ex2_approx(fmaf(s[4 * j + 0], c, neg));
-                    const float p1 = ex2_approx(fmaf(s[4 * j + 1], c, neg));
-                    const float p2 = ex2_approx(fmaf(s[4 * j + 2], c, neg));
-                    const float p3 = ex2_approx(fmaf(s[4 * j + 3], c, neg));
-                    l0 += p0, l1 += p1, l2 += p2, l3 += p3;
-                    pw[j] = pack_e4m3x4(p0, p1, p2, p3);
+                for (int i = 0; i < BS / 4; ++i) {
+                    const float2 p01 = exp_pair(2 * i), p23 = exp_pair(2 * i + 1);
+                    la = __fadd2_rn(la, p01);
+                    lb = __fadd2_rn(lb, p23);
+                    pw[i] = pack_e4m3x4(p01.x, p01.y, p23.x, p23.y);
                 }
-                tmem_st_x32(s_addr, pw);
+                tmem_st_u16(s_addr, pw);
             } else if constexpr (C::PMODE == QA_P_E4M3_HILO) {
-                uint32_t hi[32], lo[32];
+                uint32_t hi[BS / 4], lo[BS / 4];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float p0 = ex2_approx(fmaf(s[4 * j + 0], c, neg));
-                    const float p1 = ex2_approx(fmaf(s[4 * j + 1], c, neg));
-                    const float p2 = ex2_approx(fmaf(s[4 * j + 2], c, neg));
-                    const float p3 = ex2_approx(fmaf(s[4 * j + 3], c, neg));
-                    l0 += p0, l1 += p1, l2 += p2, l3 += p3;
-                    const uint32_t h01 = cvt_e4m3x2(p0, p1), h23 = cvt_e4m3x2(p2, p3);
+                for (int i = 0; i < BS / 4; ++i) {
+                    const float2 p01 = exp_pair(2 * i), p23 = exp_pair(2 * i + 1);
+                    la = __fadd2_rn(la, p01);
+                    lb = __fadd2_rn(lb, p23);
+                    const uint32_t h01 = cvt_e4m3x2(p01.x, p01.y), h23 = cvt_e4m3x2(p23.x, p23.y);
                     const float2 f01 = e4m3x2_to_float2(h01), f23 = e4m3x2_to_float2(h23);
-                    hi[j] = h01 | (h23 << 16);
-                    lo[j] = pack_e4m3x4(p0 - f01.x, p1 - f01.y, p2 - f23.x, p3 - f23.y);
+                    hi[i] = h01 | (h23 << 16);
+                    lo[i] = pack_e4m3x4(p01.x - f01.x, p01.y - f01.y, p23.x - f23.x, p23.y - f23.y);
                 }
-                tmem_st_x32(s_addr, hi);
-                tmem_st_x32(s_addr + C::TM_P_LO, lo);
+                tmem_st_u16(s_addr, hi);
+                tmem_st_u16(s_addr + C::TM_P_LO, lo);
             } else {
-                uint32_t pw[64];
+                uint32_t pw[BS / 2];
 #pragma unroll
-                for (int j = 0; j < 64; j += 2) {
-                    const float p0 = ex2_approx(fmaf(s[2 * j + 0], c, neg));
-                    const float p1 = ex2_approx(fmaf(s[2 * j + 1], c, neg));
-                    const float p2 = ex2_approx(fmaf(s[2 * j + 2], c, neg));
-                    const float p3 = ex2_approx(fmaf(s[2 * j + 3], c, neg));
-                    l0 += p0, l1 += p1, l2 += p2, l3 += p3;
-                    pw[j] = p.out_fp16 ? pack_f16x2(p0, p1) : pack_bf16x2(p0, p1);
-                    pw[j + 1] = p.out_fp16 ? pack_f16x2(p2, p3) : pack_bf16x2(p2, p3);
+                for (int i = 0; i < BS / 2; i += 2) {
+                    const float2 p01 = exp_pair(i), p23 = exp_pair(i + 1);
+                    la = __fadd2_rn(la, p01);
+                    lb = __fadd2_rn(lb, p23);
+                    pw[i] = p.out_fp16 ? pack_f16x2(p01.x, p01.y) : pack_bf16x2(p01.x, p01.y);
+                    pw[i + 1] = p.out_fp16 ? pack_f16x2(p23.x, p23.y) : pack_bf16x2(p23.x, p23.y);
                 }
-                tmem_st_x32(s_addr, *reinterpret_cast<uint32_t(*)[32]>(&pw[0]));
-                tmem_st_x32(s_addr + 32, *reinterpret_cast<uint32_t(*)[32]>(&pw[32]));
+                tmem_st_u32(s_addr, pw);
             }
-            l += (l0 + l1) + (l2 + l3);
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(&bars->p_full[t]);
+            mbar_arrive(&bars->p_full[t][j & 1]);
         }
+        const float l = (la.x + la.y) + (lb.x + lb.y);
 
         // ---------------------------------------------------------------- epilogue: O / l -> 16 bit -> smem -> TMA
         mbar_wait(&bars->o_full[t], 0);
@@ -405,9 +487,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             tmem_ld_wait();
             uint32_t w[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const float a = o[2 * j] * inv, bb = o[2 * j + 1] * inv;
-                w[j] = p.out_fp16 ? pack_f16x2(a, bb) : pack_bf16x2(a, bb);
+            for (int i = 0; i < 16; ++i) {
+                const float a = o[2 * i] * inv, bb = o[2 * i + 1] * inv;
+                w[i] = p.out_fp16 ? pack_f16x2(a, bb) : pack_bf16x2(a, bb);
             }
             // 64 output columns (128 bytes) per box row, 128B-swizzled so the TMA store un-swizzles it
             uint8_t* box = o_smem + (cc >> 6) * (BM * 128) + row * 128;
