@@ -9,19 +9,22 @@
 //   CTA = 2 query tiles of 128 rows, 12 warps (3 warpgroups; setmaxnreg moves registers to the softmax warps):
 //     warps 0-3  softmax + (rare) O rescale + epilogue of query tile 0   (thread r <-> TMEM lane r <-> query row r)
 //     warps 4-7  the same for query tile 1
-//     warp  8    MMA issuer (one thread)
-//     warp  9    TMA producer: Q once, K/V tiles of 128 keys through mbarrier rings      (warps 10-11 idle)
-//   The softmax / MMA hand-off runs in STEPS of 64 keys, and every query tile owns TWO score buffers in TMEM:
-//   while the softmax warps work on S_j the tensor core already holds S_{j+1}, and QK_{j+2} / PV_j are issued
-//   the moment P_j lands.  The softmax chain never waits for an MMA in steady state, which matters because at
-//   D = 128 the exp unit (MUFU, 16 / clk / SM), not the tensor pipe, is the tighter bound of FP8 attention.
+//     warp  8/10 MMA issuer of query tile 0 / 1 (one elected thread each)
+//     warp  9    TMA producer: Q once, K/V tiles of 128 keys through mbarrier rings      (warp 11 idle)
+//   The softmax / MMA hand-off runs in STEPS of 64 keys.  Per query tile TMEM holds ONE score buffer S and TWO
+//   P buffers: a softmax thread pulls its S_j row into registers and releases the buffer at once (s_free), so
+//   QK_{j+1} runs under the exponentials of step j; P_j goes to its own buffer, so PV_j never blocks a QK.
+//   Inside a softmax warp the step is software-pipelined: the load of S_{j+1} and its row maximum are
+//   interleaved with the last exponentials of step j, so a warp issues MUFU work almost without gaps.  That
+//   matters because at D = 128 the exp unit (MUFU, 16 / clk / SM), not the tensor pipe, bounds FP8 attention.
 //   To go past that bound a compile-time fraction of the exponentials is evaluated on the FMA pipe
 //   (Cody-Waite split + minimax polynomial, packed fp32x2 arithmetic) instead of MUFU.EX2.
-//   TMEM (512 columns): S(t,b) at t*128 + b*64 | O_t at 256 + t*128; P_j aliases the first columns of its S buffer.
+//   TMEM (512 columns): S_t at t*128 | P(t,b) at t*128 + 64 + b*32 | O_t at 256 + t*128.
 //   K and V tiles are shared by both query tiles, halving L2->SMEM traffic per FLOP.
 //
 // Deliberately absent: any non-sm_100 path, any fallback.
 #include <cmath>
+#include <type_traits>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include "ptx.cuh"
@@ -29,6 +32,17 @@
 #include "tma_host.h"
 
 namespace qa {
+
+#ifdef QA_TRACE
+long long* g_trace_ptr = nullptr;
+#define QA_STAMP(role, step, ev)                                                                   \
+    do {                                                                                          \
+        if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && (step) < 80) \
+            p.trace[((role) * 80 + (step)) * 8 + (ev)] = clock64();                               \
+    } while (0)
+#else
+#define QA_STAMP(role, step, ev) do { } while (0)
+#endif
 
 constexpr int BM = 128;  // query rows per tile (= TMEM lanes)
 constexpr int BN = 128;  // keys per K/V shared-memory tile (one TMA box)
@@ -67,11 +81,12 @@ struct AttnCfg {
     static constexpr int SMEM_O = (NQ == 2) ? SMEM_V + STAGES * V_TILE : SMEM_K;
     static constexpr int SMEM_BAR = (NQ == 2) ? SMEM_O + NQ * O_TILE : SMEM_V + STAGES * V_TILE;
     static_assert(NQ == 2 || STAGES * K_TILE >= O_TILE, "K ring too small to stage O");
-    static constexpr int SMEM_TOTAL = SMEM_BAR + 256 + 1024;  // + barriers + alignment slack
+    static constexpr int SMEM_TOTAL = SMEM_BAR + 512 + 1024;  // + barriers + alignment slack
     static_assert(SMEM_TOTAL <= 232448, "shared memory budget exceeded");
     static constexpr int NTHREADS = (NQ * 4 + 4) * 32;  // softmax warpgroups + one warpgroup holding the MMA / TMA warps
     // TMEM columns
-    static constexpr int TM_S = 0;                        // S(t, b) at t * 128 + b * 64
+    static constexpr int TM_S = 0;                        // S_t at t * 128 (64 columns)
+    static constexpr int TM_P = 64;                       // P(t, b) at t * 128 + 64 + b * 32
     static constexpr int TM_O = 256;                      // O_t at 256 + t * 128 (D <= 128), single O at D = 256
     static constexpr int TM_P_LO = 16;                    // hi/lo mode: second P tile 16 columns after the first
     // softmax range management: p' = 2^KOFF * exp2(s - m_used), m_used may lag the true max by <= TAU (log2 units)
@@ -92,16 +107,18 @@ struct AttnParams {
     float sm_scale_log2;  // sm_scale * log2(e)
     int out_fp16;
     float inv_group;  // Hkv / Hq
+    long long* trace;  // developer builds (-DQA_TRACE): per-step clock64 stamps of CTA (0,0,0), else unused
 };
 
 struct Barriers {
     uint64_t q_full[2];
     uint64_t k_full[4], k_empty[4], v_full[4], v_empty[4];
-    uint64_t s_full[2][2], p_full[2][2];  // [tile][score buffer]
-    uint64_t pv_done[2], o_full[2];
+    uint64_t s_full[2], s_free[2];  // [tile]: S_j written by the tensor core / pulled into registers by the softmax
+    uint64_t p_full[2][2];          // [tile][P buffer]
+    uint64_t pv_done[2][2], o_full[2];  // pv_done[tile][step parity]: PV_j complete
     uint32_t tmem_base;
 };
-static_assert(sizeof(Barriers) <= 256, "barrier block too large");
+static_assert(sizeof(Barriers) <= 512, "barrier block too large");
 
 template <class C>
 __device__ __forceinline__ uint32_t qk_koff(int k) {  // byte offset of the k-th 32-byte K slice inside a Q/K tile
@@ -177,18 +194,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     if (threadIdx.x == 32) {
         for (int t = 0; t < 2; ++t) {
             mbar_init(&bars->q_full[t], 1);
-            mbar_init(&bars->pv_done[t], 1);
+            mbar_init(&bars->pv_done[t][0], 1);
+            mbar_init(&bars->pv_done[t][1], 1);
             mbar_init(&bars->o_full[t], 1);
-            for (int bb = 0; bb < 2; ++bb) {
-                mbar_init(&bars->s_full[t][bb], 1);
-                mbar_init(&bars->p_full[t][bb], 128);
-            }
+            mbar_init(&bars->s_full[t], 1);
+            mbar_init(&bars->s_free[t], 128);
+            for (int bb = 0; bb < 2; ++bb) mbar_init(&bars->p_full[t][bb], 128);
         }
         for (int s = 0; s < 4; ++s) {
             mbar_init(&bars->k_full[s], 1);
-            mbar_init(&bars->k_empty[s], 1);
+            mbar_init(&bars->k_empty[s], NQ);  // released by every tile's MMA warp
             mbar_init(&bars->v_full[s], 1);
-            mbar_init(&bars->v_empty[s], 1);
+            mbar_init(&bars->v_empty[s], NQ);
         }
         fence_barrier_init();
     }
@@ -232,35 +249,38 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                                     x * (C::V_ROW / C::VB), n * BN, bhkv, kEvictLast);
                 }
             }
-        } else if (warp == NQ * 4) {
-            // =========================================================== MMA issuer
-            // The whole warp walks the loop converged (so addresses and descriptors stay on the uniform datapath);
-            // one elected lane issues the tcgen05 instructions.  Descriptors are built once: per MMA only the
-            // 14-bit start-address field of the low word changes.
+        } else if (warp == NQ * 4 || (NQ == 2 && warp == NQ * 4 + 2)) {
+            // =========================================================== MMA issuers: one warp per query tile
+            // Each tile has its own chain  P_j -> PV_j -> QK_{j+2} -> S_{j+2}; a warp per tile keeps the two chains
+            // independent (a single in-order issuer would couple them) and halves the per-step instruction stream.
+            // The warp walks the loop converged; one elected lane issues.  Descriptors are built once: per MMA only
+            // the 14-bit start-address field of the low word changes.
+            const int t = (warp - NQ * 4) >> 1;
+            const int nst = n_steps(t);
             constexpr uint32_t idesc_qk = make_idesc(0, 0, 0, 0, BM, BS);
             constexpr uint32_t idesc_pv8 = make_idesc(0, 0, 0, 1, BM, D);
             const uint32_t idesc_pv = C::V16 ? make_idesc(p.out_fp16 ? 0 : 1, p.out_fp16 ? 0 : 1, 0, 1, BM, D) : idesc_pv8;
             constexpr uint64_t qk_swz = (C::QK_ROW == 128) ? kSwz128 : kSwz64;
             constexpr uint64_t v_swz = (C::V_ROW == 128) ? kSwz128 : kSwz64;
-            const uint64_t q_desc0 = make_smem_desc(smem_u32(smem + C::SMEM_Q), 16, 8 * C::QK_ROW, qk_swz);
+            const uint64_t q_desc = make_smem_desc(smem_u32(smem + C::SMEM_Q + t * C::Q_TILE), 16, 8 * C::QK_ROW, qk_swz);
             const uint64_t k_desc0 = make_smem_desc(smem_u32(smem + C::SMEM_K), 16, 8 * C::QK_ROW, qk_swz);
             const uint64_t v_desc0 = make_smem_desc(smem_u32(smem + C::SMEM_V), C::V_BOX_BYTES, 8 * C::V_ROW, v_swz);
             constexpr int KEYS_PER_PV = C::V16 ? 16 : 32;
+            const uint32_t s_t = C::TM_S + t * 128;
+            const uint32_t p_t0 = C::TM_P + t * 128;
+            const uint32_t o_t = C::TM_O + (NQ == 2 ? t * 128 : 0);
 
-            // S(t, j & 1) = Q_t . K[keys of step j]^T : 64 key rows starting at (j & 1) * 64 of the K tile
-            auto issue_qk = [&](int t, int stage, int j) {
-                const uint32_t s_t = C::TM_S + t * 128 + (j & 1) * BS;
-                const uint64_t ad = q_desc0 + uint64_t((t * C::Q_TILE) >> 4);
-                const uint64_t bd = k_desc0 + uint64_t((stage * C::K_TILE + (j & 1) * (BS * C::QK_ROW)) >> 4);
+            // S_t = Q_t . K[64 keys]^T, the keys being rows [half * 64, half * 64 + 64) of K stage `stage`
+            auto issue_qk = [&](int stage, int half) {
+                const uint64_t bd = k_desc0 + uint64_t((stage * C::K_TILE + half * (BS * C::QK_ROW)) >> 4);
 #pragma unroll
                 for (int k = 0; k < D / 32; ++k)
-                    umma_f8_ss(s_t, ad + (qk_koff<C>(k) >> 4), bd + (qk_koff<C>(k) >> 4), idesc_qk, k > 0);
+                    umma_f8_ss(s_t, q_desc + (qk_koff<C>(k) >> 4), bd + (qk_koff<C>(k) >> 4), idesc_qk, k > 0);
             };
-            // O_t (+)= P_j . V[keys of step j]
-            auto issue_pv = [&](int t, int stage, int j, bool acc) {
-                const uint32_t o_t = C::TM_O + (NQ == 2 ? t * 128 : 0);
-                const uint32_t p_t = C::TM_S + t * 128 + (j & 1) * BS;
-                const uint64_t bd = v_desc0 + uint64_t((stage * C::V_TILE + (j & 1) * (BS * C::V_ROW)) >> 4);
+            // O_t (+)= P(t, half) . V[64 keys]
+            auto issue_pv = [&](int stage, int half, bool acc) {
+                const uint32_t p_t = p_t0 + half * 32;
+                const uint64_t bd = v_desc0 + uint64_t((stage * C::V_TILE + half * (BS * C::V_ROW)) >> 4);
 #pragma unroll
                 for (int k = 0; k < BS / KEYS_PER_PV; ++k) {
                     const uint64_t bk = bd + uint64_t((k * KEYS_PER_PV * C::V_ROW) >> 4);
@@ -273,73 +293,89 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 }
             };
 
-            // prologue: the first two score buffers of every tile come from K tile 0
+            // prologue: S_0 and (once S_0 has been pulled) S_1 from K tile 0
+            mbar_wait(&bars->q_full[t], 0);
             mbar_wait(&bars->k_full[0], 0);
-            for (int t = 0; t < NQ; ++t) {
-                mbar_wait(&bars->q_full[t], 0);
+            tc_fence_after();
+            if (elect_one()) {
+                issue_qk(0, 0);
+                umma_commit(&bars->s_full[t]);
+                if (nst == 1) umma_commit(&bars->k_empty[0]);
+            }
+            __syncwarp();
+            if (nst > 1) {
+                mbar_wait(&bars->s_free[t], 0);
                 tc_fence_after();
                 if (elect_one()) {
-                    issue_qk(t, 0, 0);
-                    umma_commit(&bars->s_full[t][0]);
+                    issue_qk(0, 1);
+                    umma_commit(&bars->s_full[t]);
+                    umma_commit(&bars->k_empty[0]);
                 }
                 __syncwarp();
             }
-            for (int t = 0; t < NQ; ++t) {
-                if (1 < n_steps(t)) {
+
+            // steady state, one K/V tile (two steps) per trip; the score GEMM runs two steps ahead of the PV GEMM:
+            //   [s_free(j+1) -> QK_{j+2}]  [p_full(j) -> PV_j]  [s_free(j+2) -> QK_{j+3}]  [p_full(j+1) -> PV_{j+1}]
+            int sv = 0, sk = 0;       // ring slots of the V tile feeding PV_j and of the K tile feeding QK_{j+2}
+            uint32_t pv = 0, pk = 0;  // their parities
+            uint32_t pp = 0;          // parity of p_full[t][*] (both buffers flip once per trip)
+            for (int j = 0; j < nst; j += 2) {
+                const bool has1 = j + 1 < nst, has2 = j + 2 < nst, has3 = j + 3 < nst;
+                if (++sk == C::STAGES) sk = 0, pk ^= 1;
+                if (has2) {
+                    // ---- QK_{j+2}: first half of the next K tile
+                    mbar_wait(&bars->k_full[sk], pk);
+                    mbar_wait(&bars->s_free[t], 1);
+                    tc_fence_after();
                     if (elect_one()) {
-                        issue_qk(t, 0, 1);
-                        umma_commit(&bars->s_full[t][1]);
+                        issue_qk(sk, 0);
+                        umma_commit(&bars->s_full[t]);
+                        if (!has3) umma_commit(&bars->k_empty[sk]);
                     }
                     __syncwarp();
                 }
-            }
-            if (elect_one()) umma_commit(&bars->k_empty[0]);
-            __syncwarp();
-
-            for (int j = 0; j < n_max; ++j) {
-                const int kt = j >> 1;
-                const int sv = kt % C::STAGES;
-                if ((j & 1) == 0) {
-                    mbar_wait(&bars->v_full[sv], (kt / C::STAGES) & 1);
-                    tc_fence_after();
-                }
-                const int jn = j + 2;
-                const int ktn = jn >> 1;
-                const int skn = ktn % C::STAGES;
-                bool k_ready = (jn & 1) != 0;  // the odd step's K tile was waited for one iteration earlier
-#pragma unroll
-                for (int t = 0; t < NQ; ++t) {
-                    if (j < n_steps(t)) {
-                        mbar_wait(&bars->p_full[t][j & 1], (j >> 1) & 1);
-                        tc_fence_after();
-                        if (elect_one()) {
-                            issue_pv(t, sv, j, j > 0);
-                            umma_commit(&bars->pv_done[t]);
-                        }
-                        __syncwarp();
-                    }
-                    if (jn < n_steps(t)) {
-                        if (!k_ready) {
-                            mbar_wait(&bars->k_full[skn], (ktn / C::STAGES) & 1);
-                            tc_fence_after();
-                            k_ready = true;
-                        }
-                        if (elect_one()) {
-                            issue_qk(t, skn, jn);
-                            umma_commit(&bars->s_full[t][jn & 1]);
-                        }
-                        __syncwarp();
-                    }
-                }
+                QA_STAMP(2 + t, j, 0);
+                // ---- PV_j: P buffer 0, first half of the V tile
+                mbar_wait(&bars->v_full[sv], pv);
+                mbar_wait(&bars->p_full[t][0], pp);
+                tc_fence_after();
+                QA_STAMP(2 + t, j, 1);
                 if (elect_one()) {
-                    if ((j & 1) == 1 || j == n_max - 1) umma_commit(&bars->v_empty[sv]);
-                    if (jn < n_max && ((jn & 1) == 1 || jn == n_max - 1)) umma_commit(&bars->k_empty[skn]);
+                    issue_pv(sv, 0, j > 0);
+                    umma_commit(&bars->pv_done[t][0]);
+                    if (!has1) umma_commit(&bars->v_empty[sv]);
                 }
                 __syncwarp();
+                QA_STAMP(2 + t, j, 2);
+                if (has3) {
+                    // ---- QK_{j+3}: second half of that K tile
+                    mbar_wait(&bars->s_free[t], 0);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        issue_qk(sk, 1);
+                        umma_commit(&bars->s_full[t]);
+                        umma_commit(&bars->k_empty[sk]);
+                    }
+                    __syncwarp();
+                }
+                if (has1) {
+                    QA_STAMP(2 + t, j + 1, 0);
+                    // ---- PV_{j+1}: P buffer 1, second half of the V tile
+                    mbar_wait(&bars->p_full[t][1], pp);
+                    tc_fence_after();
+                    QA_STAMP(2 + t, j + 1, 1);
+                    if (elect_one()) {
+                        issue_pv(sv, 1, true);
+                        umma_commit(&bars->pv_done[t][1]);
+                        umma_commit(&bars->v_empty[sv]);
+                    }
+                    __syncwarp();
+                    QA_STAMP(2 + t, j + 1, 2);
+                }
+                pp ^= 1;
+                if (++sv == C::STAGES) sv = 0, pv ^= 1;
             }
-            if (elect_one()) {
-                for (int t = 0; t < NQ; ++t) umma_commit(&bars->o_full[t]);
-            }
+            if (elect_one()) umma_commit(&bars->o_full[t]);
             __syncwarp();
         }
     } else {
@@ -348,7 +384,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const int t = warp >> 2;                       // query tile of this warpgroup
         const int row = ((warp & 3) << 5) | lane;      // row inside the tile == TMEM lane
         const uint32_t lane_base = uint32_t((warp & 3) * 32) << 16;
-        const uint32_t s_base = tmem + lane_base + C::TM_S + t * 128;
+        const uint32_t s_addr = tmem + lane_base + C::TM_S + t * 128;
+        const uint32_t p_base = tmem + lane_base + C::TM_P + t * 128;
         const uint32_t o_addr = tmem + lane_base + C::TM_O + (NQ == 2 ? t * 128 : 0);
         const int row_g = m0 + t * BM + row;
 
@@ -365,13 +402,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);  // running sum of p' (4 partial sums)
         const int my_steps = n_steps(t);
 
-        for (int j = 0; j < my_steps; ++j) {
-            const uint32_t s_addr = s_base + (j & 1) * BS;
-            mbar_wait(&bars->s_full[t][j & 1], (j >> 1) & 1);
-            tc_fence_after();
-            float s[BS];
-            tmem_ld_f64(s_addr, s);
-            tmem_ld_wait();
+        // per-column K scales (token mode) and the causal / ragged mask, applied to the raw scores of step j
+        auto fixup = [&](const int j, float (&s)[BS]) {
             const int col0 = j * BS;
             if constexpr (TOKEN) {
                 if (col0 + BS <= p.Skv && (p.Skv & 3) == 0) {  // rows of scale_k stay 16-byte aligned
@@ -394,13 +426,26 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 for (int i = 0; i < BS; ++i)
                     if (col0 + i > lim) s[i] = -INFINITY;
             }
-            float mx0 = fmaxf(s[0], s[1]), mx1 = fmaxf(s[2], s[3]);
+        };
+        // row maximum of sixteen columns folded into two running maxima (two chains per call site -> four in flight)
+        auto max16 = [&](const float (&s)[BS], int q, float& ma, float& mb) {
 #pragma unroll
-            for (int i = 4; i < BS; i += 4) {
-                mx0 = fmaxf(mx0, fmaxf(s[i], s[i + 1]));
-                mx1 = fmaxf(mx1, fmaxf(s[i + 2], s[i + 3]));
+            for (int i = 16 * q; i < 16 * q + 16; i += 4) {
+                ma = fmaxf(ma, fmaxf(s[i], s[i + 1]));
+                mb = fmaxf(mb, fmaxf(s[i + 2], s[i + 3]));
             }
-            const float m_new = fmaxf(m_used, fmaxf(mx0, mx1));
+        };
+
+        // One 64-key step.  On entry `s` holds S_j (already fixed up) and `mx` its row maximum.  The step turns S_j
+        // into P_j.  Unless it is the LAST step it also pulls S_{j+1} into `s_next` three quarters of the way
+        // through, frees the score buffer for QK_{j+2}, and folds the row maximum of S_{j+1} into its last
+        // exponentials; it returns that maximum.  The code between the few waits is straight-line on purpose:
+        // every branch is a scheduling barrier at which the exp pipeline of this warp drains.
+        auto step = [&](const int j, float (&s)[BS], float (&s_next)[BS], const float mx, auto last_tag) -> float {
+            constexpr bool LAST = decltype(last_tag)::value;
+            QA_STAMP(t, j, 0);
+            const float m_new = fmaxf(m_used, mx);
+            bool p_prev_pending = j > 0;  // P_{j-1} is stored but not yet published (see below)
             // lazy rescale: keep the stale max while the true max has grown by < 2^TAU
             const bool grow = (m_new - m_used) * c > C::TAU;
             if (__any_sync(0xffffffffu, grow)) {
@@ -408,8 +453,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 m_used = m_new;
                 la.x *= alpha, la.y *= alpha, lb.x *= alpha, lb.y *= alpha;
                 if (j > 0) {
-                    // O_t must be quiescent: PV_{j-1} is the only MMA that can still be writing it
-                    mbar_wait(&bars->pv_done[t], (j - 1) & 1);
+                    // O_t must be quiescent: PV_{j-1} is the only MMA that can still be writing it - and it cannot
+                    // even start before P_{j-1} is published
+                    tmem_st_wait();
+                    tc_fence_before();
+                    mbar_arrive(&bars->p_full[t][(j - 1) & 1]);
+                    p_prev_pending = false;
+                    // (one barrier per step parity: PV_{j-3}, the previous phase of this barrier, is known to be
+                    // complete because S_j has been seen, so the parity test cannot alias)
+                    mbar_wait(&bars->pv_done[t][(j - 1) & 1], ((j - 1) >> 1) & 1);
                     tc_fence_after();
 #pragma unroll
                     for (int cc = 0; cc < D; cc += 32) {
@@ -420,10 +472,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                         for (int i = 0; i < 32; ++i) o[i] *= alpha;
                         tmem_st_x32(o_addr + cc, o);
                     }
+                    tmem_st_wait();
                 }
             }
             const float neg = C::KOFF - m_used * c;
             const float2 neg2 = make_float2(neg, neg);
+            QA_STAMP(t, j, 1);
 
             // p' for one pair of columns; a compile-time subset of the pairs avoids MUFU
             auto exp_pair = [&](int i) -> float2 {
@@ -431,46 +485,115 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 if (pair_uses_poly(i, C::POLY_NUM)) return exp2_poly<C::POLY_DEG>(x);
                 return make_float2(ex2_approx(x.x), ex2_approx(x.y));
             };
-
-            if constexpr (C::PMODE == QA_P_E4M3) {
-                uint32_t pw[BS / 4];
-#pragma unroll
-                for (int i = 0; i < BS / 4; ++i) {
-                    const float2 p01 = exp_pair(2 * i), p23 = exp_pair(2 * i + 1);
-                    la = __fadd2_rn(la, p01);
-                    lb = __fadd2_rn(lb, p23);
+            uint32_t pw[C::V16 ? BS / 2 : BS / 4], pw_lo[C::PMODE == QA_P_E4M3_HILO ? BS / 4 : 1];
+            // four columns -> P words
+            auto exp_quad = [&](int i) {
+                const float2 p01 = exp_pair(2 * i), p23 = exp_pair(2 * i + 1);
+                la = __fadd2_rn(la, p01);
+                lb = __fadd2_rn(lb, p23);
+                if constexpr (C::PMODE == QA_P_E4M3) {
                     pw[i] = pack_e4m3x4(p01.x, p01.y, p23.x, p23.y);
-                }
-                tmem_st_u16(s_addr, pw);
-            } else if constexpr (C::PMODE == QA_P_E4M3_HILO) {
-                uint32_t hi[BS / 4], lo[BS / 4];
-#pragma unroll
-                for (int i = 0; i < BS / 4; ++i) {
-                    const float2 p01 = exp_pair(2 * i), p23 = exp_pair(2 * i + 1);
-                    la = __fadd2_rn(la, p01);
-                    lb = __fadd2_rn(lb, p23);
+                } else if constexpr (C::PMODE == QA_P_E4M3_HILO) {
                     const uint32_t h01 = cvt_e4m3x2(p01.x, p01.y), h23 = cvt_e4m3x2(p23.x, p23.y);
                     const float2 f01 = e4m3x2_to_float2(h01), f23 = e4m3x2_to_float2(h23);
-                    hi[i] = h01 | (h23 << 16);
-                    lo[i] = pack_e4m3x4(p01.x - f01.x, p01.y - f01.y, p23.x - f23.x, p23.y - f23.y);
+                    pw[i] = h01 | (h23 << 16);
+                    pw_lo[i] = pack_e4m3x4(p01.x - f01.x, p01.y - f01.y, p23.x - f23.x, p23.y - f23.y);
+                } else {
+                    pw[2 * i] = p.out_fp16 ? pack_f16x2(p01.x, p01.y) : pack_bf16x2(p01.x, p01.y);
+                    pw[2 * i + 1] = p.out_fp16 ? pack_f16x2(p23.x, p23.y) : pack_bf16x2(p23.x, p23.y);
                 }
-                tmem_st_u16(s_addr, hi);
-                tmem_st_u16(s_addr + C::TM_P_LO, lo);
-            } else {
-                uint32_t pw[BS / 2];
+            };
+
 #pragma unroll
-                for (int i = 0; i < BS / 2; i += 2) {
-                    const float2 p01 = exp_pair(i), p23 = exp_pair(i + 1);
-                    la = __fadd2_rn(la, p01);
-                    lb = __fadd2_rn(lb, p23);
-                    pw[i] = p.out_fp16 ? pack_f16x2(p01.x, p01.y) : pack_bf16x2(p01.x, p01.y);
-                    pw[i + 1] = p.out_fp16 ? pack_f16x2(p23.x, p23.y) : pack_bf16x2(p23.x, p23.y);
-                }
-                tmem_st_u32(s_addr, pw);
+            for (int i = 0; i < 2; ++i) exp_quad(i);
+            if (p_prev_pending) {  // P_{j-1} was stored at the end of the previous step: publish it now
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(&bars->p_full[t][(j - 1) & 1]);
             }
-            tmem_st_wait();
+#pragma unroll
+            for (int i = 2; i < 12; ++i) exp_quad(i);
+            float ma = -INFINITY, mb = -INFINITY;
+            if constexpr (!LAST) {
+                // S_{j+1} was issued by the tensor core when this thread released S_j, about one step ago
+                mbar_wait(&bars->s_full[t], (j + 1) & 1);
+                tc_fence_after();
+                tmem_ld_f64(s_addr, s_next);
+                QA_STAMP(t, j, 2);
+#pragma unroll
+                for (int i = 12; i < 14; ++i) exp_quad(i);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(&bars->s_free[t]);  // the score buffer may be overwritten by QK_{j+2}
+                fixup(j + 1, s_next);
+                QA_STAMP(t, j, 3);
+#pragma unroll
+                for (int i = 14; i < 16; ++i) {
+                    exp_quad(i);
+                    max16(s_next, 2 * (i - 14), ma, mb);
+                    max16(s_next, 2 * (i - 14) + 1, ma, mb);
+                }
+            } else {
+#pragma unroll
+                for (int i = 12; i < 16; ++i) exp_quad(i);
+                // P buffer reuse: PV_{j-2} must have drained it.  Seeing S_{j+1} (issued after PV_{j-2}, in-order
+                // tensor pipe) proves that in every other step; the last one waits for PV_{j-1} explicitly.
+                if (j >= 2) mbar_wait(&bars->pv_done[t][(j - 1) & 1], ((j - 1) >> 1) & 1);
+            }
+            const uint32_t p_addr = p_base + (j & 1) * 32;
+            if constexpr (C::PMODE == QA_P_E4M3) {
+                tmem_st_u16(p_addr, pw);
+            } else if constexpr (C::PMODE == QA_P_E4M3_HILO) {
+                tmem_st_u16(p_addr, pw);
+                tmem_st_u16(p_addr + C::TM_P_LO, pw_lo);
+            } else {
+                tmem_st_u32(p_addr, pw);
+            }
+            if constexpr (LAST) {  // nothing left to hide the store behind
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(&bars->p_full[t][j & 1]);
+            }
+            QA_STAMP(t, j, 4);
+            return fmaxf(ma, mb);
+        };
+
+#ifdef QA_STAGGER
+        if (t == 1) {  // start the second tile's softmax out of phase with the first
+            const long long t_go = clock64() + QA_STAGGER;
+            while (clock64() < t_go) {
+            }
+        }
+#endif
+        float s_a[BS], s_b[BS];
+        float mx;
+        {   // S_0
+            mbar_wait(&bars->s_full[t], 0);
+            tc_fence_after();
+            tmem_ld_f64(s_addr, s_a);
+            tmem_ld_wait();
             tc_fence_before();
-            mbar_arrive(&bars->p_full[t][j & 1]);
+            mbar_arrive(&bars->s_free[t]);
+            fixup(0, s_a);
+            float ma = -INFINITY, mb = -INFINITY;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) max16(s_a, q, ma, mb);
+            mx = fmaxf(ma, mb);
+        }
+        {
+            using std::false_type;
+            using std::true_type;
+            int j = 0;
+            for (; j + 2 < my_steps; j += 2) {
+                mx = step(j, s_a, s_b, mx, false_type{});
+                mx = step(j + 1, s_b, s_a, mx, false_type{});
+            }
+            if (j + 1 < my_steps) {  // two steps left
+                mx = step(j, s_a, s_b, mx, false_type{});
+                step(j + 1, s_b, s_a, mx, true_type{});
+            } else {                 // one step left
+                step(j, s_a, s_b, mx, true_type{});
+            }
         }
         const float l = (la.x + la.y) + (lb.x + lb.y);
 
@@ -553,6 +676,11 @@ static int launch_cfg(const AttnArgs& a, cudaStream_t stream, int* launches) {
     p.sm_scale_log2 = a.sm_scale * kLog2e;
     p.out_fp16 = (a.out_dtype == QA_DT_FP16);
     p.inv_group = float(a.Hkv) / float(a.Hq);
+#ifdef QA_TRACE
+    p.trace = g_trace_ptr;
+#else
+    p.trace = nullptr;
+#endif
 
     auto kern = attn_fwd_kernel<C, CAUSAL, TOKEN>;
     static bool attr_done = false;  // per instantiation; racing threads set the same value
@@ -586,6 +714,10 @@ static int launch_d(const AttnArgs& a, cudaStream_t stream, int* launches) {
     }
     return set_error(QA_ERR_INVALID, "Unsupported head dimension: %d", a.D);
 }
+#endif
+
+#ifdef QA_TRACE
+extern "C" void qa_debug_set_trace(void* dev_ptr) { g_trace_ptr = static_cast<long long*>(dev_ptr); }
 #endif
 
 int attn_fwd_dispatch(const AttnArgs& a, cudaStream_t stream, int* launches) {

@@ -1,0 +1,116 @@
+// Developer microbenchmark (not product code): how fast can 1..4 warps per SM sub-partition run the softmax
+// instruction stream of attn_fwd.cu on registers only (no TMEM, no barriers)?   nvcc -arch=sm_100a -O3 -o softmax_rate
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../quantumattention_b200/csrc/ptx.cuh"
+using namespace qa;
+
+template <int DEG>
+__device__ __forceinline__ float2 exp2_poly(float2 x) {
+    x.x = fmaxf(x.x, -125.f);
+    x.y = fmaxf(x.y, -125.f);
+    const float2 t = __fadd2_rn(x, make_float2(12582912.f, 12582912.f));
+    const float2 n = __fadd2_rn(t, make_float2(-12582912.f, -12582912.f));
+    const float2 f = __ffma2_rn(n, make_float2(-1.f, -1.f), x);
+    float2 q;
+    if constexpr (DEG == 2) {
+        q = __ffma2_rn(f, make_float2(0.23842893540859222f, 0.23842893540859222f), make_float2(0.7034479975700378f, 0.7034479975700378f));
+        q = __ffma2_rn(q, f, make_float2(1.0004431009292603f, 1.0004431009292603f));
+    } else {
+        q = __ffma2_rn(f, make_float2(0.0551716685295105f, 0.0551716685295105f), make_float2(0.2426111251115799f, 0.2426111251115799f));
+        q = __ffma2_rn(q, f, make_float2(0.6932609677314758f, 0.6932609677314758f));
+        q = __ffma2_rn(q, f, make_float2(0.9999280571937561f, 0.9999280571937561f));
+    }
+    float2 r;
+    r.x = __int_as_float(__float_as_int(q.x) + (__float_as_int(t.x) << 23));
+    r.y = __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23));
+    return r;
+}
+__host__ __device__ constexpr bool pair_uses_poly(int i, int num) { return (((i & 7) + 1) * num) / 8 > ((i & 7) * num) / 8; }
+
+// MODE 0: MUFU only.  1: scale + MUFU + sum + cvt/pack (the exp phase).  2: mode 1 + the max pass.
+template <int MODE, int POLY>
+__global__ void __launch_bounds__(512, 1) k(const float* __restrict__ in, uint32_t* __restrict__ out, long long* cyc, int rounds) {
+    float s[64];
+    for (int i = 0; i < 64; ++i) s[i] = in[(threadIdx.x * 64 + i) & 4095];
+    float2 la = make_float2(0.f, 0.f), lb = la;
+    uint32_t acc = 0;
+    float c = in[5], neg = in[6];
+    const float2 c2 = make_float2(c, c);
+    __syncthreads();
+    long long t0 = clock64();
+    for (int r = 0; r < rounds; ++r) {
+        if (MODE == 2) {
+            float m0 = s[0], m1 = s[1];
+#pragma unroll
+            for (int i = 0; i < 64; i += 4) { m0 = fmaxf(m0, fmaxf(s[i], s[i + 1])); m1 = fmaxf(m1, fmaxf(s[i + 2], s[i + 3])); }
+            neg = fminf(neg, -fmaxf(m0, m1) * 1e-30f);
+        }
+        const float2 neg2 = make_float2(neg, neg);
+        uint32_t pw[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            float2 p01, p23;
+            if (MODE == 0) {
+                p01 = make_float2(ex2_approx(s[4 * i]), ex2_approx(s[4 * i + 1]));
+                p23 = make_float2(ex2_approx(s[4 * i + 2]), ex2_approx(s[4 * i + 3]));
+                s[4 * i] = p01.x; s[4 * i + 1] = p01.y; s[4 * i + 2] = p23.x; s[4 * i + 3] = p23.y;
+            } else {
+                float2 x01 = __ffma2_rn(make_float2(s[4 * i], s[4 * i + 1]), c2, neg2);
+                float2 x23 = __ffma2_rn(make_float2(s[4 * i + 2], s[4 * i + 3]), c2, neg2);
+                p01 = pair_uses_poly(2 * i, POLY) ? exp2_poly<2>(x01) : make_float2(ex2_approx(x01.x), ex2_approx(x01.y));
+                p23 = pair_uses_poly(2 * i + 1, POLY) ? exp2_poly<2>(x23) : make_float2(ex2_approx(x23.x), ex2_approx(x23.y));
+                la = __fadd2_rn(la, p01);
+                lb = __fadd2_rn(lb, p23);
+                pw[i] = pack_e4m3x4(p01.x, p01.y, p23.x, p23.y);
+            }
+        }
+        if (MODE != 0) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc ^= pw[i];
+            // keep the inputs changing so nothing is hoisted
+#pragma unroll
+            for (int i = 0; i < 64; i += 16) s[i] = __int_as_float(__float_as_int(s[i]) ^ (acc & 1));
+        }
+    }
+    long long t1 = clock64();
+    float sum = la.x + la.y + lb.x + lb.y;
+    for (int i = 0; i < 64; ++i) sum += s[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc + __float_as_int(sum);
+    if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
+template <int MODE, int POLY>
+void run(const char* name, int warps, const float* in, uint32_t* out, long long* cyc) {
+    const int rounds = 200;
+    k<MODE, POLY><<<148, warps * 32>>>(in, out, cyc, rounds);
+    k<MODE, POLY><<<148, warps * 32>>>(in, out, cyc, rounds);
+    cudaDeviceSynchronize();
+    long long h[148];
+    cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
+    double avg = 0;
+    for (int i = 0; i < 148; ++i) avg += h[i];
+    avg /= 148;
+    // cycles per (64-column step of one warp); MUFU-bound = 64 * 8 * warps_per_smsp / (1 - poly fraction)
+    printf("%-28s warps/SM %2d  cycles/step/warp %7.1f   per-SMSP cycles per warp-step %7.1f\n", name, warps, avg / rounds,
+           avg / rounds / (warps / 4.0));
+}
+
+int main() {
+    float* in; uint32_t* out; long long* cyc;
+    cudaMalloc(&in, 4096 * 4); cudaMalloc(&out, 148 * 512 * 4); cudaMalloc(&cyc, 148 * 8);
+    float h[4096];
+    for (int i = 0; i < 4096; ++i) h[i] = -0.001f * (i % 977);
+    h[5] = 0.7f; h[6] = -0.5f;
+    cudaMemcpy(in, h, sizeof(h), cudaMemcpyHostToDevice);
+    for (int w : {4, 8, 16}) run<0, 0>("mufu only", w, in, out, cyc);
+    for (int w : {4, 8, 16}) run<1, 0>("exp phase poly0", w, in, out, cyc);
+    for (int w : {4, 8, 16}) run<2, 0>("max+exp poly0", w, in, out, cyc);
+    for (int w : {4, 8, 16}) run<2, 1>("max+exp poly1/8", w, in, out, cyc);
+    for (int w : {4, 8, 16}) run<2, 2>("max+exp poly2/8", w, in, out, cyc);
+    for (int w : {4, 8, 16}) run<2, 3>("max+exp poly3/8", w, in, out, cyc);
+    for (int w : {4, 8, 16}) run<2, 4>("max+exp poly4/8", w, in, out, cyc);
+    printf("%s\n", cudaGetErrorString(cudaGetLastError()));
+    return 0;
+}
