@@ -324,6 +324,27 @@ def main():
         e2e_ms = float(t.item())
     e2e_value = world * fl / (e2e_ms / args.e2e_steps * 1e-3) / 1e12
 
+    # ---- the quantiser alone (HBM-bound leg of the step): Q, K, V of one input set per launch, rotating sets
+    quant_ms = None
+    if rank == 0:
+        qmode = _native.QA_SCALE_HEAD
+        for i in range(3):
+            _native.quantize_fp8(list(sets[i % n_sets]), qmode)
+        torch.cuda.synchronize()
+        _native.quant_events = []
+        for i in range(50):
+            _native.quantize_fp8(list(sets[i % n_sets]), qmode)
+        torch.cuda.synchronize()
+        qev, _native.quant_events = _native.quant_events, None
+        quant_ms = statistics.mean(a.elapsed_time(b) for a, b in qev)  # memset + kernel, per call, on the stream
+        # host-side cost of one step (python + ctypes + allocator), GPU not waited for
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(50):
+            step(i)
+        host_us = (time.perf_counter() - t0) / 50 * 1e6
+        torch.cuda.synchronize()
+
     # ---- the other two P modes, kernel only (context for the headline mode; 20 launches each)
     other_modes = {}
     if rank == 0:
@@ -369,6 +390,18 @@ def main():
         "attn_kernel_ms": attn_ms, "flops_per_launch": fl,
         "exp_bound_tflops_at_max_clock": 148 * 16 * 1.965e9 * 4 * D / 1e12,
     }
+    quant_bytes = 3 * B * H * S * D * 3 + 3 * B * H * 4  # 2 B in + 1 B out per element, + scales
+    quantiser = {
+        "kernel": "quant_head_fused_kernel (+ workspace memset)", "bound": "hbm", "ms": quant_ms,
+        "achieved": quant_bytes / (quant_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+        "frac": quant_bytes / (quant_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes": quant_bytes,
+        "traffic": None,
+    }
+    try:
+        tq = json.load(open(tpath)).get("quantiser", {})
+        quantiser["traffic"] = tq.get("quant_head_fused_kernel")
+    except Exception:
+        pass
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -377,6 +410,8 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 3 * B * H * S * D * 2,
                 "d2h_bytes_per_step": B * H * S * D * 2, "ms_per_step": e2e_ms / args.e2e_steps},
         "roofline": roofline,
+        "quantiser": quantiser,
+        "host_us_per_step": host_us,
         "per_gpu_tflops": value / world,
         "frac_of_fp8_spec": value / world / FP8_SPEC_TFLOPS,
         "other_pv_modes_kernel_tflops": other_modes,

@@ -34,6 +34,8 @@ extern "C" {
 /* scale granularity (reference: "head-wise" src/quantum_attn/nn.py:411-412, "token-wise" :413-414) */
 #define QA_SCALE_HEAD 0  /* one fp32 scale per (b, h):        scale[B*H]     */
 #define QA_SCALE_TOKEN 1 /* one fp32 scale per (b, h, token): scale[B*H*S]   */
+#define QA_SCALE_HEAD_TWO_PASS 2 /* qa_quantize_fp8 only: QA_SCALE_HEAD results through the two-pass kernels (the path
+                                    heads longer than one resident wave take by themselves); for tests */
 
 /* how P = softmax(QK^T) is fed to the second GEMM */
 #define QA_P_E4M3 0      /* P -> e4m3, V e4m3, tcgen05 kind::f8f6f4               (north-star fast path)          */
@@ -65,8 +67,10 @@ int qa_device_supported(int dev);
  *   x_strides   4 element strides per tensor (x_strides[4*i .. 4*i+3]); the last one must be 1, rows 16-byte aligned
  *   x8[i]       out: dense e4m3 bytes [B, H, S[i], D]
  *   scale[i]    out: fp32 [B*H] (QA_SCALE_HEAD) or [B*H*S[i]] (QA_SCALE_TOKEN)
- *   amax_ws     scratch, 3 * B * H floats (QA_SCALE_HEAD only; may be NULL for token mode); need not be zeroed
+ *   amax_ws     scratch of qa_quantize_workspace_floats(B, H, max_i S[i], D) floats, 8-byte aligned (head-wise only;
+ *               may be NULL for token mode); need not be zeroed, must not be shared by calls that can run concurrently
  */
+size_t qa_quantize_workspace_floats(int B, int H, int max_S, int D);
 int qa_quantize_fp8(int n_tensors, const void* const* x, int x_dtype, const int64_t* x_strides, void* const* x8,
                     float* const* scale, float* amax_ws, int B, int H, const int* S, int D, int scale_mode,
                     void* stream);

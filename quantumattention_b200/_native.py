@@ -14,7 +14,7 @@ import torch
 from . import build as _build
 
 QA_DT_BF16, QA_DT_FP16, QA_DT_E4M3 = 0, 1, 2
-QA_SCALE_HEAD, QA_SCALE_TOKEN = 0, 1
+QA_SCALE_HEAD, QA_SCALE_TOKEN, QA_SCALE_HEAD_TWO_PASS = 0, 1, 2
 QA_P_E4M3, QA_P_E4M3_HILO, QA_P_16BIT = 0, 1, 2
 ABI_VERSION = 1
 
@@ -22,6 +22,7 @@ EXPORTED_SYMBOLS = (
     "qa_abi_version",
     "qa_last_error",
     "qa_device_supported",
+    "qa_quantize_workspace_floats",
     "qa_quantize_fp8",
     "qa_fp8_attn_fwd",
     "qa_last_launch_count",
@@ -34,6 +35,7 @@ _lock = threading.Lock()
 # attention kernel (events are recorded on the launching stream; a few hundred ns each)
 launch_total = 0
 attn_events = None  # set to a list to collect (start_event, stop_event) pairs
+quant_events = None  # the same for the quantiser launches
 
 
 class NativeError(RuntimeError):
@@ -71,6 +73,8 @@ def load(build_if_missing: bool = True):
             ctypes.c_int, vp,
         ]
         lib.qa_quantize_fp8.restype = ctypes.c_int
+        lib.qa_quantize_workspace_floats.argtypes = [ctypes.c_int] * 4
+        lib.qa_quantize_workspace_floats.restype = ctypes.c_size_t
         lib.qa_fp8_attn_fwd.argtypes = [
             vp, vp, vp, ctypes.c_int, vp, vp, vp, ctypes.c_int, vp, ctypes.c_int, vp,
             ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
@@ -123,9 +127,10 @@ def quantize_fp8(tensors: Sequence[torch.Tensor], scale_mode: int) -> Tuple[list
             t = t.contiguous()
         xs.append(t)
     outs = [torch.empty(t.shape, dtype=torch.float8_e4m3fn, device=dev) for t in xs]
-    if scale_mode == QA_SCALE_HEAD:
+    if scale_mode in (QA_SCALE_HEAD, QA_SCALE_HEAD_TWO_PASS):
         scales = [torch.empty((B, H), dtype=torch.float32, device=dev) for _ in xs]
-        ws = torch.empty((3 * B * H,), dtype=torch.float32, device=dev)
+        n_ws = int(lib.qa_quantize_workspace_floats(B, H, max(t.shape[2] for t in xs), D))
+        ws = torch.empty((n_ws,), dtype=torch.float32, device=dev)
         ws_ptr = ws.data_ptr()
     else:
         scales = [torch.empty((B, H, t.shape[2]), dtype=torch.float32, device=dev) for t in xs]
@@ -137,9 +142,16 @@ def quantize_fp8(tensors: Sequence[torch.Tensor], scale_mode: int) -> Tuple[list
     strides = (ctypes.c_int64 * (4 * n))(*[s for t in xs for s in t.stride()])
     S = (ctypes.c_int * n)(*[t.shape[2] for t in xs])
     with torch.cuda.device(dev):
-        stream = torch.cuda.current_stream(dev).cuda_stream
+        tstream = torch.cuda.current_stream(dev)
+        stream = tstream.cuda_stream
+        if quant_events is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(tstream)
         rc = lib.qa_quantize_fp8(n, x_arr, _dt_code(t0.dtype), strides, o_arr, s_arr, ws_ptr, B, H, S, D,
                                  scale_mode, stream)
+        if quant_events is not None:
+            ev1.record(tstream)
+            quant_events.append((ev0, ev1))
     _check(rc, "qa_quantize_fp8")
     global launch_total
     launch_total += int(lib.qa_last_launch_count())

@@ -59,6 +59,14 @@ int qa_device_supported(int dev) {
     return 1;
 }
 
+size_t qa_quantize_workspace_floats(int B, int H, int max_S, int D) {
+    // two-pass kernels: amax cells [3BH] (+ spare);  single-pass kernel: one 8-byte slot per 32 KB slab of 3 tensors
+    if (B < 1 || H < 1 || max_S < 1 || D < 1) return 0;
+    const size_t slab_rows = 32768 / (size_t(D) * 2) ? 32768 / (size_t(D) * 2) : 1;
+    const size_t slabs = (size_t(max_S) + slab_rows - 1) / slab_rows * 3 * size_t(B) * size_t(H);
+    return size_t(6) * size_t(B) * size_t(H) + 8 + 2 * slabs;
+}
+
 int qa_quantize_fp8(int n_tensors, const void* const* x, int x_dtype, const int64_t* x_strides, void* const* x8,
                     float* const* scale, float* amax_ws, int B, int H, const int* S, int D, int scale_mode,
                     void* stream) {
@@ -67,6 +75,8 @@ int qa_quantize_fp8(int n_tensors, const void* const* x, int x_dtype, const int6
     if (!x || !x_strides || !x8 || !scale || !S) return set_error(QA_ERR_INVALID, "null argument array");
     if (x_dtype != QA_DT_BF16 && x_dtype != QA_DT_FP16)
         return set_error(QA_ERR_INVALID, "x_dtype must be bf16 or fp16");
+    const bool two_pass = scale_mode == QA_SCALE_HEAD_TWO_PASS;
+    if (two_pass) scale_mode = QA_SCALE_HEAD;
     if (scale_mode != QA_SCALE_HEAD && scale_mode != QA_SCALE_TOKEN)
         return set_error(QA_ERR_INVALID, "Unsupported scaling_method code: %d", scale_mode);
     if (D != 64 && D != 128 && D != 256) return set_error(QA_ERR_INVALID, "Unsupported head dimension: %d", D);
@@ -90,6 +100,10 @@ int qa_quantize_fp8(int n_tensors, const void* const* x, int x_dtype, const int6
     }
     a.B = B, a.H = H, a.D = D;
     a.amax_ws = amax_ws;
+    a.force_two_pass = two_pass ? 1 : 0;
+    int max_S = 0;
+    for (int i = 0; i < n_tensors; ++i) max_S = S[i] > max_S ? S[i] : max_S;
+    a.ws_floats = qa_quantize_workspace_floats(B, H, max_S, D);
     int rc = check_device();
     if (rc != QA_OK) return rc;
     return quantize_dispatch(a, x_dtype, scale_mode, n_tensors, static_cast<cudaStream_t>(stream), &g_launches);

@@ -15,6 +15,8 @@ struct QuantArgs {
     int B, H, D;
     float* amax_ws;
     int rows_per_cta;
+    int force_two_pass;
+    size_t ws_floats;
 };
 
 struct AttnArgs {

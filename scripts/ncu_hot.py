@@ -1,24 +1,17 @@
-#!/usr/bin/env python
-"""Top stall sites from `ncu -i X.ncu-rep --page source --csv` (SASS view)."""
-import csv, subprocess, sys, collections
-rep = sys.argv[1]; topn = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
-rows = list(csv.reader(out.splitlines()))
-hdr = rows[1]; data = rows[2:]
-ia, isrc, isamp, iex = hdr.index("Address"), hdr.index("Source"), hdr.index("# Samples"), hdr.index("Instructions Executed")
-stalls = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
-tot = sum(int(r[isamp]) for r in data)
-print("total samples", tot, "total inst", sum(int(r[iex]) for r in data))
-opc = collections.Counter()
-for r in data:
-    toks = r[isrc].split()
-    op = toks[1] if toks[0].startswith("@") else toks[0]
-    opc[op.split(".")[0]] += int(r[iex])
-print("inst mix:", opc.most_common(25))
-agg = collections.Counter()
-for r in data:
-    for i in stalls: agg[hdr[i]] += int(r[i])
-print("stall totals:", agg.most_common(12))
-for idx, r in sorted(enumerate(data), key=lambda t: -int(t[1][isamp]))[:topn]:
-    st = sorted(((int(r[i]), hdr[i][6:]) for i in stalls if int(r[i])), reverse=True)[:3]
-    print(f"{idx:5d} {int(r[isamp]):6d} {100*int(r[isamp])/tot:5.1f}% ex={r[iex]:>8} {r[isrc].strip()[:70]:70s} {st}")
+"""scripts/ncu_hot.py REPORT.csv [N]: hottest SASS instructions of an `ncu --page source --csv` export, with their stall mix."""
+import csv, sys
+rows = list(csv.reader(open(sys.argv[1])))
+hdr = rows[1]
+col = {n: i for i, n in enumerate(hdr)}
+body = [r for r in rows[2:] if len(r) == len(hdr)]
+tot = sum(int(r[col["# Samples"]] or 0) for r in body)
+stalls = [n for n in hdr if n.startswith("stall_") and "Not Issued" not in n]
+agg = {s: sum(int(r[col[s]] or 0) for r in body) for s in stalls}
+print("total samples", tot, " instructions", len(body))
+print("stall mix:", {k[6:]: round(100 * v / tot, 1) for k, v in sorted(agg.items(), key=lambda kv: -kv[1]) if v > tot * 0.005})
+N = int(sys.argv[2]) if len(sys.argv) > 2 else 40
+top = sorted(body, key=lambda r: -int(r[col["# Samples"]] or 0))[:N]
+for r in sorted(top, key=lambda r: r[col["Address"]]):
+    s = int(r[col["# Samples"]] or 0)
+    mix = sorted(((int(r[col[k]] or 0), k[6:]) for k in stalls), reverse=True)[:3]
+    print(f"{r[col['Address']][-5:]} {100*s/tot:5.2f}% ex={r[col['Instructions Executed']]:>9} {r[col['Source']][:70]:70s} {[(n, c) for c, n in mix if c]}")

@@ -12,13 +12,15 @@ from conftest import bf16_from_bits
 
 pytestmark = pytest.mark.gpu
 
-MODES = {"head-wise": _native.QA_SCALE_HEAD, "token-wise": _native.QA_SCALE_TOKEN}
+# "head-wise-2pass": same function through the two-pass kernels (what heads longer than one resident wave take)
+MODES = {"head-wise": _native.QA_SCALE_HEAD, "token-wise": _native.QA_SCALE_TOKEN,
+         "head-wise-2pass": _native.QA_SCALE_HEAD_TWO_PASS}
 
 
 def _check(x_cpu: torch.Tensor, mode: str):
     (x8,), (scale,) = _native.quantize_fp8([x_cpu.cuda()], MODES[mode])
     torch.cuda.synchronize()
-    b, s = oracle.quantize_fp8(x_cpu.float().numpy(), mode)
+    b, s = oracle.quantize_fp8(x_cpu.float().numpy(), mode.replace("-2pass", ""))
     got = x8.view(torch.uint8).cpu().numpy()
     assert got.shape == b.shape
     nbad = int((got != b).sum())
@@ -35,7 +37,7 @@ def test_golden_vectors_from_reference(golden_dir, mode, file):
     assert np.array_equal(scale.cpu().numpy(), g["scale"])
 
 
-@pytest.mark.parametrize("mode", ["head-wise", "token-wise"])
+@pytest.mark.parametrize("mode", ["head-wise", "token-wise", "head-wise-2pass"])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("shape", [(2, 8, 512, 64), (1, 3, 999, 128), (1, 2, 1000, 256), (1, 1, 1, 64), (2, 2, 17, 128)])
 def test_random_inputs(mode, dtype, shape):
@@ -45,7 +47,7 @@ def test_random_inputs(mode, dtype, shape):
 
 
 @pytest.mark.parametrize("kind", ["outlier_channels", "huge_token", "zero_head"])
-@pytest.mark.parametrize("mode", ["head-wise", "token-wise"])
+@pytest.mark.parametrize("mode", ["head-wise", "token-wise", "head-wise-2pass"])
 def test_stress_inputs(kind, mode):
     q, k, v = oracle.make_qkv(1, 3, 300, 300, 128, seed=5, kind=kind)
     for t in (q, k, v):
@@ -55,7 +57,7 @@ def test_stress_inputs(kind, mode):
 def test_three_tensors_one_launch_and_ragged_lengths():
     q, k, v = oracle.make_qkv(2, 4, 333, 470, 128, seed=9)
     (q8, k8, v8), (sq, sk, sv) = _native.quantize_fp8([q.cuda(), k.cuda(), v.cuda()], _native.QA_SCALE_HEAD)
-    assert _native.last_launch_count() == 2
+    assert _native.last_launch_count() == 1  # single-pass head-wise kernel, Q, K and V in one launch
     for t, t8, s in ((q, q8, sq), (k, k8, sk), (v, v8, sv)):
         b, sc = oracle.quantize_fp8(t.float().numpy(), "head-wise")
         assert np.array_equal(t8.view(torch.uint8).cpu().numpy(), b)
@@ -107,3 +109,48 @@ def test_full_size_checksum_flux_shape():
     # compare on the fp32 path instead: quantise(deq) in torch with the same formula
     y2 = (deq / scale[:, :, None, None]).clamp(-448, 448).to(torch.float8_e4m3fn)
     assert torch.equal(y2.view(torch.uint8), x8.view(torch.uint8))
+
+
+def test_single_pass_matches_two_pass_at_flux_size():
+    """C2-sized tensors (36 CTAs per head, 2592 CTAs): the per-head arrival protocol against the two-pass kernels."""
+    q, k, v = oracle.make_qkv(1, 24, 4608, 4608, 128, seed=3)
+    xs = [q.cuda(), k.cuda(), v.cuda()]
+    for _ in range(3):  # repeated calls: the workspace is re-zeroed per call
+        a8, asc = _native.quantize_fp8(xs, _native.QA_SCALE_HEAD)
+    assert _native.last_launch_count() == 1
+    b8, bsc = _native.quantize_fp8(xs, _native.QA_SCALE_HEAD_TWO_PASS)
+    assert _native.last_launch_count() == 2
+    for x8, y8, s1, s2 in zip(a8, b8, asc, bsc):
+        assert torch.equal(x8.view(torch.uint8), y8.view(torch.uint8))
+        assert torch.equal(s1, s2)
+    b, sc = oracle.quantize_fp8(q[:, :2].float().numpy(), "head-wise")
+    assert np.array_equal(a8[0][:, :2].view(torch.uint8).cpu().numpy(), b)
+    assert np.array_equal(asc[0][:, :2].cpu().numpy(), sc)
+
+
+def test_long_head_takes_two_pass_path():
+    """A head of 150k tokens at D=64 exceeds one resident wave even with 16 passes per CTA -> two launches."""
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(1, 1, 400_000, 64, generator=g).to(torch.bfloat16)
+    (x8,), (scale,) = _native.quantize_fp8([x.cuda()], _native.QA_SCALE_HEAD)
+    n = _native.last_launch_count()
+    b, sc = oracle.quantize_fp8(x.float().numpy(), "head-wise")
+    assert np.array_equal(x8.view(torch.uint8).cpu().numpy(), b) and np.array_equal(scale.cpu().numpy(), sc)
+    assert n in (1, 2)
+
+
+def test_quotient_is_correctly_rounded_for_adversarial_scales():
+    """The reciprocal-plus-two-corrections quotient must equal IEEE division: bytes identical to the oracle for scales
+    whose mantissa is all ones / just above a power of two (worst cases for reciprocal rounding), and every bf16
+    magnitude below amax as the numerator."""
+    bits = torch.arange(0, 0x7F80, dtype=torch.int32).to(torch.int16)  # every non-negative finite bf16
+    allv = bits.view(torch.bfloat16).float()
+    for amax in (448.0 * 1.99999988, 448.0 * 1.00000012, 3.0, 0.333251953125, 1.0e-3, 57344.0, 1.00390625):
+        amax_bf = torch.tensor(amax).to(torch.bfloat16).float().item()
+        vals = allv[allv <= amax_bf]
+        n = (vals.numel() // 64) * 64
+        x = vals[-n:].clone()
+        x[-1] = amax_bf
+        x = torch.cat([x, -x]).reshape(1, 1, -1, 64).to(torch.bfloat16)
+        _check(x, "head-wise")
+        _check(x, "token-wise")
