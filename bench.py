@@ -172,6 +172,7 @@ def main():
     ap.add_argument("--pv-mode", default=None, choices=["fp8", "fp8_hilo", "16bit"])
     ap.add_argument("--e2e-steps", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-modes", action="store_true", help="skip the kernel-only numbers of the other P modes")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -347,7 +348,7 @@ def main():
 
     # ---- the other two P modes, kernel only (context for the headline mode; 20 launches each)
     other_modes = {}
-    if rank == 0:
+    if rank == 0 and not args.no_other_modes:
         for mode in ("fp8", "fp8_hilo", "16bit"):
             if mode == pv_mode:
                 continue

@@ -35,9 +35,10 @@ namespace qa {
 
 #ifdef QA_TRACE
 long long* g_trace_ptr = nullptr;
+int g_trace_x = 0, g_trace_y = 0;
 #define QA_STAMP(role, step, ev)                                                                   \
     do {                                                                                          \
-        if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && (step) < 80) \
+        if (p.trace && blockIdx.x == p.trace_x && blockIdx.y == p.trace_y && blockIdx.z == 0 && lane == 0 && (step) < 80) \
             p.trace[((role) * 80 + (step)) * 8 + (ev)] = clock64();                               \
     } while (0)
 #else
@@ -51,6 +52,9 @@ constexpr float kLog2e = 1.4426950408889634f;
 
 #ifndef QA_POLY_NUM
 #define QA_POLY_NUM 2  // of every 8 pairs of exponentials, how many run on the FMA pipe instead of MUFU
+#endif
+#ifndef QA_LOADQ
+#define QA_LOADQ 12    // S_{j+1} is pulled into registers after this many (of 16) quads of step j's exponentials
 #endif
 
 template <int D_, int PMODE_>
@@ -107,7 +111,8 @@ struct AttnParams {
     float sm_scale_log2;  // sm_scale * log2(e)
     int out_fp16;
     float inv_group;  // Hkv / Hq
-    long long* trace;  // developer builds (-DQA_TRACE): per-step clock64 stamps of CTA (0,0,0), else unused
+    long long* trace;  // developer builds (-DQA_TRACE): per-step clock64 stamps of one CTA, else unused
+    int trace_x, trace_y;
 };
 
 struct Barriers {
@@ -186,26 +191,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int n_max = n_steps(NQ - 1);
     const int n_kv = (n_max + 1) >> 1;  // K/V tiles of 128 keys
 
+    QA_STAMP(warp >> 2, 78, 0);
     // ------------------------------------------------------------------ one-time setup
     if (warp == 0) {
         tmem_alloc(&bars->tmem_base, 512);
         tmem_relinquish();
     }
-    if (threadIdx.x == 32) {
-        for (int t = 0; t < 2; ++t) {
-            mbar_init(&bars->q_full[t], 1);
-            mbar_init(&bars->pv_done[t][0], 1);
-            mbar_init(&bars->pv_done[t][1], 1);
-            mbar_init(&bars->o_full[t], 1);
-            mbar_init(&bars->s_full[t], 1);
-            mbar_init(&bars->s_free[t], 128);
-            for (int bb = 0; bb < 2; ++bb) mbar_init(&bars->p_full[t][bb], 128);
-        }
-        for (int s = 0; s < 4; ++s) {
-            mbar_init(&bars->k_full[s], 1);
-            mbar_init(&bars->k_empty[s], NQ);  // released by every tile's MMA warp
-            mbar_init(&bars->v_full[s], 1);
-            mbar_init(&bars->v_empty[s], NQ);
+    if (warp == 1) {  // one barrier per lane
+        if (lane < 4) {
+            const int t = lane >> 1, x = lane & 1;
+            mbar_init(x ? &bars->o_full[t] : &bars->q_full[t], 1);
+            mbar_init(&bars->pv_done[t][x], 1);
+            mbar_init(&bars->p_full[t][x], 128);
+            mbar_init(x ? &bars->s_free[t] : &bars->s_full[t], x ? 128 : 1);
+        } else if (lane < 8) {
+            const int st = lane - 4;
+            mbar_init(&bars->k_full[st], 1);
+            mbar_init(&bars->k_empty[st], NQ);  // released by every tile's MMA warp
+            mbar_init(&bars->v_full[st], 1);
+            mbar_init(&bars->v_empty[st], NQ);
         }
         fence_barrier_init();
     }
@@ -402,10 +406,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);  // running sum of p' (4 partial sums)
         const int my_steps = n_steps(t);
 
-        // per-column K scales (token mode) and the causal / ragged mask, applied to the raw scores of step j
-        auto fixup = [&](const int j, float (&s)[BS]) {
-            const int col0 = j * BS;
+        // per-column K scales (token mode), applied to the raw scores of step j
+        auto kscale = [&](const int j, float (&s)[BS]) {
             if constexpr (TOKEN) {
+                const int col0 = j * BS;
                 if (col0 + BS <= p.Skv && (p.Skv & 3) == 0) {  // rows of scale_k stay 16-byte aligned
 #pragma unroll
                     for (int i = 0; i < BS; i += 4) {
@@ -417,7 +421,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     for (int i = 0; i < BS; ++i) s[i] *= __ldg(sk_row + min(col0 + i, p.Skv - 1));
                 }
             }
-            // masking: only steps that touch the causal diagonal or the ragged tail pay for it
+        };
+        // causal / ragged mask of step j.  Only the trailing steps of a tile can need it (the ragged tail is the last
+        // step, the causal diagonal the last two), so it is instantiated in the tail loop only: the main loop below
+        // carries no mask code at all and stays a compact straight line for the instruction cache.
+        auto mask = [&](const int j, float (&s)[BS]) {
+            const int col0 = j * BS;
             const bool tail = col0 + BS > p.Skv;
             const bool diag = CAUSAL && (col0 + BS - 1 > m0 + t * BM);
             if (tail || diag) {
@@ -427,6 +436,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     if (col0 + i > lim) s[i] = -INFINITY;
             }
         };
+        // first step whose scores need the mask (every later one does too)
+        const int j_mask = CAUSAL ? min(p.Skv / BS, (m0 + t * BM) / BS) : p.Skv / BS;
         // row maximum of sixteen columns folded into two running maxima (two chains per call site -> four in flight)
         auto max16 = [&](const float (&s)[BS], int q, float& ma, float& mb) {
 #pragma unroll
@@ -435,20 +446,37 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 mb = fmaxf(mb, fmaxf(s[i + 2], s[i + 3]));
             }
         };
+        // rare: the running maximum of some row of this warp grew by more than 2^TAU -> rescale O (rolled: cold code)
+        auto rescale_o = [&](const float alpha) {
+#pragma unroll 1
+            for (int cc = 0; cc < D; cc += 32) {
+                float o[32];
+                tmem_ld_x32(o_addr + cc, o);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o[i] *= alpha;
+                tmem_st_x32(o_addr + cc, o);
+            }
+            tmem_st_wait();
+        };
 
-        // One 64-key step.  On entry `s` holds S_j (already fixed up) and `mx` its row maximum.  The step turns S_j
-        // into P_j.  Unless it is the LAST step it also pulls S_{j+1} into `s_next` three quarters of the way
-        // through, frees the score buffer for QK_{j+2}, and folds the row maximum of S_{j+1} into its last
-        // exponentials; it returns that maximum.  The code between the few waits is straight-line on purpose:
-        // every branch is a scheduling barrier at which the exp pipeline of this warp drains.
-        auto step = [&](const int j, float (&s)[BS], float (&s_next)[BS], const float mx, auto last_tag) -> float {
-            constexpr bool LAST = decltype(last_tag)::value;
+        // One 64-key step.  On entry `s` holds S_j (scaled / masked as needed) and `mx` its row maximum.  The step turns
+        // S_j into P_j.  Unless it is the last step it also pulls S_{j+1} into `s_next` after LOADQ quads of
+        // exponentials, frees the score buffer for QK_{j+2}, and folds the row maximum of S_{j+1} into the remaining
+        // exponentials; it returns that maximum.  The code between the few waits is straight-line on purpose: every
+        // branch is a scheduling barrier at which the exp pipeline of this warp drains.
+        //   MASKED (compile time): S_{j+1} may need the causal / ragged mask;  `last`: there is no S_{j+1}.
+        constexpr int LOADQ = QA_LOADQ;  // quad index (of 16) before which the load of S_{j+1} is issued
+        static_assert(LOADQ >= 2 && LOADQ <= 12 && LOADQ % 2 == 0, "LOADQ");
+        auto step = [&](const int j, float (&s)[BS], float (&s_next)[BS], const float mx, auto mask_tag,
+                        const bool last) -> float {
+            constexpr bool MASKED = decltype(mask_tag)::value;
             QA_STAMP(t, j, 0);
             const float m_new = fmaxf(m_used, mx);
             bool p_prev_pending = j > 0;  // P_{j-1} is stored but not yet published (see below)
             // lazy rescale: keep the stale max while the true max has grown by < 2^TAU
             const bool grow = (m_new - m_used) * c > C::TAU;
-            if (__any_sync(0xffffffffu, grow)) {
+            if (__builtin_expect(__any_sync(0xffffffffu, grow), 0)) {
                 const float alpha = ex2_approx((m_used - m_new) * c);  // 0 on the first step
                 m_used = m_new;
                 la.x *= alpha, la.y *= alpha, lb.x *= alpha, lb.y *= alpha;
@@ -463,16 +491,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     // complete because S_j has been seen, so the parity test cannot alias)
                     mbar_wait(&bars->pv_done[t][(j - 1) & 1], ((j - 1) >> 1) & 1);
                     tc_fence_after();
-#pragma unroll
-                    for (int cc = 0; cc < D; cc += 32) {
-                        float o[32];
-                        tmem_ld_x32(o_addr + cc, o);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) o[i] *= alpha;
-                        tmem_st_x32(o_addr + cc, o);
-                    }
-                    tmem_st_wait();
+                    rescale_o(alpha);
                 }
             }
             const float neg = C::KOFF - m_used * c;
@@ -512,30 +531,37 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 mbar_arrive(&bars->p_full[t][(j - 1) & 1]);
             }
 #pragma unroll
-            for (int i = 2; i < 12; ++i) exp_quad(i);
+            for (int i = 2; i < LOADQ; ++i) exp_quad(i);
             float ma = -INFINITY, mb = -INFINITY;
-            if constexpr (!LAST) {
+            if (!last) {
                 // S_{j+1} was issued by the tensor core when this thread released S_j, about one step ago
                 mbar_wait(&bars->s_full[t], (j + 1) & 1);
                 tc_fence_after();
                 tmem_ld_f64(s_addr, s_next);
                 QA_STAMP(t, j, 2);
 #pragma unroll
-                for (int i = 12; i < 14; ++i) exp_quad(i);
+                for (int i = LOADQ; i < LOADQ + 2; ++i) exp_quad(i);
                 tmem_ld_wait();
                 tc_fence_before();
                 mbar_arrive(&bars->s_free[t]);  // the score buffer may be overwritten by QK_{j+2}
-                fixup(j + 1, s_next);
+                kscale(j + 1, s_next);
+                if constexpr (MASKED) mask(j + 1, s_next);
                 QA_STAMP(t, j, 3);
+                // the row maximum of S_{j+1} is spread over the remaining quads, four 16-column pieces in all
+                constexpr int REST = 14 - LOADQ;              // quads left
+                constexpr int PER = (4 + REST - 1) / REST;    // pieces per quad (2 at LOADQ = 12, 1 from LOADQ <= 10)
 #pragma unroll
-                for (int i = 14; i < 16; ++i) {
+                for (int i = LOADQ + 2; i < 16; ++i) {
                     exp_quad(i);
-                    max16(s_next, 2 * (i - 14), ma, mb);
-                    max16(s_next, 2 * (i - 14) + 1, ma, mb);
+#pragma unroll
+                    for (int q = 0; q < PER; ++q) {
+                        const int piece = (i - LOADQ - 2) * PER + q;
+                        if (piece < 4) max16(s_next, piece, ma, mb);
+                    }
                 }
             } else {
 #pragma unroll
-                for (int i = 12; i < 16; ++i) exp_quad(i);
+                for (int i = LOADQ; i < 16; ++i) exp_quad(i);
                 // P buffer reuse: PV_{j-2} must have drained it.  Seeing S_{j+1} (issued after PV_{j-2}, in-order
                 // tensor pipe) proves that in every other step; the last one waits for PV_{j-1} explicitly.
                 if (j >= 2) mbar_wait(&bars->pv_done[t][(j - 1) & 1], ((j - 1) >> 1) & 1);
@@ -549,7 +575,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             } else {
                 tmem_st_u32(p_addr, pw);
             }
-            if constexpr (LAST) {  // nothing left to hide the store behind
+            if (last) {  // nothing left to hide the store behind
                 tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(&bars->p_full[t][j & 1]);
@@ -567,14 +593,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #endif
         float s_a[BS], s_b[BS];
         float mx;
+        QA_STAMP(t, 78, 1);
         {   // S_0
             mbar_wait(&bars->s_full[t], 0);
+            QA_STAMP(t, 78, 2);
             tc_fence_after();
             tmem_ld_f64(s_addr, s_a);
             tmem_ld_wait();
             tc_fence_before();
             mbar_arrive(&bars->s_free[t]);
-            fixup(0, s_a);
+            kscale(0, s_a);
+            mask(0, s_a);
             float ma = -INFINITY, mb = -INFINITY;
 #pragma unroll
             for (int q = 0; q < 4; ++q) max16(s_a, q, ma, mb);
@@ -583,23 +612,28 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         {
             using std::false_type;
             using std::true_type;
+            // main loop: steps whose successor exists and needs no mask, two per trip (the score registers ping-pong)
+            const int n_fast = min(my_steps - 1, j_mask - 1);
             int j = 0;
-            for (; j + 2 < my_steps; j += 2) {
-                mx = step(j, s_a, s_b, mx, false_type{});
-                mx = step(j + 1, s_b, s_a, mx, false_type{});
+            for (; j + 2 <= n_fast; j += 2) {
+                mx = step(j, s_a, s_b, mx, false_type{}, false);
+                mx = step(j + 1, s_b, s_a, mx, false_type{}, false);
             }
-            if (j + 1 < my_steps) {  // two steps left
-                mx = step(j, s_a, s_b, mx, false_type{});
-                step(j + 1, s_b, s_a, mx, true_type{});
-            } else {                 // one step left
-                step(j, s_a, s_b, mx, true_type{});
+            // tail: the few steps around the causal diagonal / ragged end, and the last one (rolled, one instance)
+#pragma unroll 1
+            for (; j < my_steps; ++j) {
+                mx = step(j, s_a, s_b, mx, true_type{}, j + 1 == my_steps);
+#pragma unroll
+                for (int i = 0; i < BS; ++i) s_a[i] = s_b[i];
             }
         }
         const float l = (la.x + la.y) + (lb.x + lb.y);
+        QA_STAMP(t, 78, 3);
 
         // ---------------------------------------------------------------- epilogue: O / l -> 16 bit -> smem -> TMA
         mbar_wait(&bars->o_full[t], 0);
         tc_fence_after();
+        QA_STAMP(t, 78, 4);
         const float sv = C::V16 ? 1.f : p.scale_v[bhkv];
         const float inv = __fdividef(sv, l);
         uint8_t* o_smem = smem + C::SMEM_O + t * C::O_TILE;
@@ -630,13 +664,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if ((warp & 3) == 0 && lane == 0 && m0 + t * BM < p.Sq) {
             for (int x = 0; x < C::O_BOXES; ++x) tma_store_3d(&tmO, o_smem + x * (BM * 128), x * 64, m0 + t * BM, bh);
             tma_store_commit();
-            tma_store_wait_all<0>();
+            tma_store_wait_read<0>();  // the CTA only has to keep its shared memory alive until it has been read
         }
+        QA_STAMP(t, 78, 5);
     }
 
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, 512);
+    QA_STAMP(warp >> 2, 78, 6);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -678,8 +714,10 @@ static int launch_cfg(const AttnArgs& a, cudaStream_t stream, int* launches) {
     p.inv_group = float(a.Hkv) / float(a.Hq);
 #ifdef QA_TRACE
     p.trace = g_trace_ptr;
+    p.trace_x = g_trace_x, p.trace_y = g_trace_y;
 #else
     p.trace = nullptr;
+    p.trace_x = p.trace_y = 0;
 #endif
 
     auto kern = attn_fwd_kernel<C, CAUSAL, TOKEN>;
@@ -718,10 +756,13 @@ static int launch_d(const AttnArgs& a, cudaStream_t stream, int* launches) {
 
 #ifdef QA_TRACE
 extern "C" void qa_debug_set_trace(void* dev_ptr) { g_trace_ptr = static_cast<long long*>(dev_ptr); }
+extern "C" void qa_debug_set_trace_cta(int x, int y) { g_trace_x = x, g_trace_y = y; }
 #endif
 
 int attn_fwd_dispatch(const AttnArgs& a, cudaStream_t stream, int* launches) {
 #ifdef QA_FAST_BUILD  // developer switch: one instantiation only, for quick ptxas / SASS inspection
+    if (a.p_mode != QA_P_E4M3 || a.D != 128 || a.causal || a.scale_mode == QA_SCALE_TOKEN)
+        return set_error(QA_ERR_INVALID, "QA_FAST_BUILD library: only D=128, fp8 P, non-causal, head-wise scales");
     return launch_cfg<AttnCfg<128, QA_P_E4M3>, false, false>(a, stream, launches);
 #else
     switch (a.p_mode) {

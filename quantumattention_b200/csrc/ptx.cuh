@@ -135,6 +135,7 @@ __device__ __forceinline__ void tma_store_wait_all() {
     asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
 
+
 // ----------------------------------------------------------------------------------------------- tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
@@ -353,8 +354,15 @@ __device__ __forceinline__ uint32_t cvt_e4m3x2(float lo, float hi) {
     asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(r) : "f"(hi), "f"(lo));
     return r;
 }
+// Four fp32 -> four e4m3 in one word.  The two halves are joined with mov.b32 {lo, hi}: ptxas then folds the join into
+// the second conversion (F2FP ... PACK_AB_MERGE_C with the first result as operand C) instead of emitting a PRMT.
 __device__ __forceinline__ uint32_t pack_e4m3x4(float a, float b, float c, float d) {
-    return cvt_e4m3x2(a, b) | (cvt_e4m3x2(c, d) << 16);
+    uint16_t lo, hi;
+    uint32_t r;
+    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(lo) : "f"(b), "f"(a));
+    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(hi) : "f"(d), "f"(c));
+    asm("mov.b32 %0, {%1, %2};" : "=r"(r) : "h"(lo), "h"(hi));
+    return r;
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     uint32_t r;

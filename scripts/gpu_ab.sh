@@ -8,7 +8,7 @@ if [ "$1" == "--tests" ]; then
 fi
 for v in "$@"; do
   wl=C2_flux
-  QA_NATIVE_LIB=$PWD/quantumattention_b200/libqattn_sm100_$v.so timeout 300 python bench.py --workload $wl --steps 300 --warmup 20 --no-cpu-baseline --e2e-steps 2 > gpurun_out/ab_$v.json 2> gpurun_out/ab_$v.err
+  QA_NATIVE_LIB=$PWD/quantumattention_b200/libqattn_sm100_$v.so timeout 300 python bench.py --workload $wl --steps 300 --warmup 20 --no-cpu-baseline --no-other-modes --e2e-steps 2 > gpurun_out/ab_$v.json 2> gpurun_out/ab_$v.err
   python - "$v" <<'PY'
 import json,sys
 v=sys.argv[1]

@@ -10,6 +10,7 @@ q, k, v = oracle.make_qkv(B, H, S, S, D, seed=0)
 (q8, k8, v8), (sq, sk, sv) = _native.quantize_fp8([q.cuda(), k.cuda(), v.cuda()], _native.QA_SCALE_HEAD)
 tr = torch.zeros(4 * 80 * 8, dtype=torch.int64, device="cuda")
 lib.qa_debug_set_trace.argtypes = [ctypes.c_void_p]
+lib.qa_debug_set_trace_cta(int(os.environ.get('TRACE_X', 0)), int(os.environ.get('TRACE_Y', 0)))
 for it in range(3):
     tr.zero_()
     lib.qa_debug_set_trace(tr.data_ptr())
@@ -17,6 +18,7 @@ for it in range(3):
     torch.cuda.synchronize()
 t = tr.cpu().view(4, 80, 8)
 t0 = int(t[t > 1000].min())
+print('t0', t0)
 def rel(x): return int(x) - t0 if int(x) > 1000 else -1
 print("step | sm0: top ldwait maxdone arrive end nr | sm1: ... | mma0: waitP gotP issued | mma1")
 for j in range(int(sys.argv[1]) if len(sys.argv) > 1 else 30):
@@ -34,3 +36,6 @@ for r, name in ((0, "sm0"), (1, "sm1")):
 for r, name in ((2, "mma0"), (3, "mma1")):
     d = t[r, 8:60]
     print(name, "waitP", float((d[:, 1] - d[:, 0]).float().mean()), "issue", float((d[:, 2] - d[:, 1]).float().mean()))
+for r in (0, 1):
+    e = [rel(t[r, 78, i]) for i in range(7)]
+    print(f"tile{r} lifecycle: entry {e[0]} setup_done {e[1]} S0_ready {e[2]} loop_end {e[3]} o_full {e[4]} stored {e[5]} exit {e[6]}")

@@ -30,7 +30,15 @@ __device__ __forceinline__ float2 exp2_poly(float2 x) {
 __host__ __device__ constexpr bool pair_uses_poly(int i, int num) { return (((i & 7) + 1) * num) / 8 > ((i & 7) * num) / 8; }
 
 // MODE 0: MUFU only.  1: scale + MUFU + sum + cvt/pack (the exp phase).  2: mode 1 + the max pass.
-template <int MODE, int POLY>
+__device__ __forceinline__ uint32_t pack4_merge(float a, float b, float c, float d) {
+    uint16_t lo, hi; uint32_t r;
+    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(lo) : "f"(b), "f"(a));
+    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(hi) : "f"(d), "f"(c));
+    asm("mov.b32 %0, {%1, %2};" : "=r"(r) : "h"(lo), "h"(hi));
+    return r;
+}
+
+template <int MODE, int POLY, bool NOSUM = false, bool MERGE = false>
 __global__ void __launch_bounds__(512, 1) k(const float* __restrict__ in, uint32_t* __restrict__ out, long long* cyc, int rounds) {
     float s[64];
     for (int i = 0; i < 64; ++i) s[i] = in[(threadIdx.x * 64 + i) & 4095];
@@ -61,9 +69,8 @@ __global__ void __launch_bounds__(512, 1) k(const float* __restrict__ in, uint32
                 float2 x23 = __ffma2_rn(make_float2(s[4 * i + 2], s[4 * i + 3]), c2, neg2);
                 p01 = pair_uses_poly(2 * i, POLY) ? exp2_poly<2>(x01) : make_float2(ex2_approx(x01.x), ex2_approx(x01.y));
                 p23 = pair_uses_poly(2 * i + 1, POLY) ? exp2_poly<2>(x23) : make_float2(ex2_approx(x23.x), ex2_approx(x23.y));
-                la = __fadd2_rn(la, p01);
-                lb = __fadd2_rn(lb, p23);
-                pw[i] = pack_e4m3x4(p01.x, p01.y, p23.x, p23.y);
+                if (!NOSUM) { la = __fadd2_rn(la, p01); lb = __fadd2_rn(lb, p23); }
+                pw[i] = MERGE ? pack4_merge(p01.x, p01.y, p23.x, p23.y) : pack_e4m3x4(p01.x, p01.y, p23.x, p23.y);
             }
         }
         if (MODE != 0) {
@@ -81,11 +88,11 @@ __global__ void __launch_bounds__(512, 1) k(const float* __restrict__ in, uint32
     if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
 
-template <int MODE, int POLY>
+template <int MODE, int POLY, bool NOSUM = false, bool MERGE = false>
 void run(const char* name, int warps, const float* in, uint32_t* out, long long* cyc) {
     const int rounds = 200;
-    k<MODE, POLY><<<148, warps * 32>>>(in, out, cyc, rounds);
-    k<MODE, POLY><<<148, warps * 32>>>(in, out, cyc, rounds);
+    k<MODE, POLY, NOSUM, MERGE><<<148, warps * 32>>>(in, out, cyc, rounds);
+    k<MODE, POLY, NOSUM, MERGE><<<148, warps * 32>>>(in, out, cyc, rounds);
     cudaDeviceSynchronize();
     long long h[148];
     cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
@@ -111,6 +118,11 @@ int main() {
     for (int w : {4, 8, 16}) run<2, 2>("max+exp poly2/8", w, in, out, cyc);
     for (int w : {4, 8, 16}) run<2, 3>("max+exp poly3/8", w, in, out, cyc);
     for (int w : {4, 8, 16}) run<2, 4>("max+exp poly4/8", w, in, out, cyc);
+    for (int w : {4, 8, 12, 16}) run<2, 2, false, true>("max+exp poly2/8 merge", w, in, out, cyc);
+    for (int w : {4, 8, 12, 16}) run<2, 2, true, true>("max+exp poly2/8 merge nosum", w, in, out, cyc);
+    for (int w : {4, 8, 12, 16}) run<2, 3, true, true>("max+exp poly3/8 merge nosum", w, in, out, cyc);
+    for (int w : {4, 8, 12, 16}) run<2, 4, true, true>("max+exp poly4/8 merge nosum", w, in, out, cyc);
+    for (int w : {4, 8, 12, 16}) run<2, 0, true, true>("max+exp poly0 merge nosum", w, in, out, cyc);
     printf("%s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
 }
