@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define QA_ABI_VERSION 1
+#define QA_ABI_VERSION 2
 
 /* element types */
 #define QA_DT_BF16 0
@@ -36,6 +36,11 @@ extern "C" {
 #define QA_SCALE_TOKEN 1 /* one fp32 scale per (b, h, token): scale[B*H*S]   */
 #define QA_SCALE_HEAD_TWO_PASS 2 /* qa_quantize_fp8 only: QA_SCALE_HEAD results through the two-pass kernels (the path
                                     heads longer than one resident wave take by themselves); for tests */
+
+#define QA_SCALE_HEAD_AMAX_ONLY 3 /* qa_quantize_fp8 only: write scale[] (from the local amax), touch no x8 (may be NULL) */
+#define QA_SCALE_HEAD_GIVEN 4     /* qa_quantize_fp8 only: scale[] is an INPUT; quantise with it.  The pair lets a caller
+                                    that shards one sequence over several GPUs take the MAX of the per-shard scales
+                                    (scale is monotone in amax) and obtain the bytes the unsharded call would produce */
 
 /* how P = softmax(QK^T) is fed to the second GEMM */
 #define QA_P_E4M3 0      /* P -> e4m3, V e4m3, tcgen05 kind::f8f6f4               (north-star fast path)          */
@@ -96,6 +101,21 @@ int qa_fp8_attn_fwd(const void* q8, const void* k8, const void* v, int v_dtype, 
                     const float* scale_k, const float* scale_v, int scale_mode, void* out, int out_dtype, float* lse,
                     int B, int Hq, int Hkv, int Sq, int Skv, int D, int causal, float sm_scale, int p_mode,
                     void* stream);
+
+/* Combine two partial attention results over disjoint key sets, row by row:
+ *     m = max(lse_acc, lse_new); w_x = exp(lse_x - m); O = (w_acc O_acc + w_new O_new) / (w_acc + w_new);
+ *     LSE = m + log(w_acc + w_new)
+ * New operator (the reference never shards a sequence; its kernel leaves the LSE output commented out,
+ * src/quantum_attn/tk/attention.py:333-346).  Used by the sequence ring for the long-video shape.
+ *
+ *   o_acc, lse_acc  running result: fp32 [rows, D] and fp32 [rows]; in/out
+ *   o_new, lse_new  partial result of one qa_fp8_attn_fwd call: 16-bit [rows, D] (o_dtype) and fp32 [rows]
+ *   out             NULL, or 16-bit [rows, D]: the merged rows are written THERE instead of into o_acc (last step)
+ *   first           != 0: the accumulator is uninitialised; the call copies (o_new, lse_new) into it
+ *   rows            B * Hq * Sq
+ */
+int qa_merge_partials(float* o_acc, float* lse_acc, const void* o_new, int o_dtype, const float* lse_new, void* out,
+                      long long rows, int D, int first, void* stream);
 
 /* Number of kernels the previous call on this thread launched (for bench.py's gpu_launches accounting). */
 int qa_last_launch_count(void);

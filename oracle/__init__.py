@@ -14,3 +14,4 @@ from .quantize_ref import dequantize, quantize_fp8  # noqa: F401
 from .attention_ref import attention_flops, cpu_reference_step, fp8_attention_ref, sdpa_ref  # noqa: F401
 from .metrics import compare  # noqa: F401
 from .inputs import CONFIGS, make_qkv  # noqa: F401
+from .ring_ref import attention_block_ref, head_scales, merge_ref, quantize_with_scale  # noqa: F401

@@ -14,9 +14,9 @@ import torch
 from . import build as _build
 
 QA_DT_BF16, QA_DT_FP16, QA_DT_E4M3 = 0, 1, 2
-QA_SCALE_HEAD, QA_SCALE_TOKEN, QA_SCALE_HEAD_TWO_PASS = 0, 1, 2
+QA_SCALE_HEAD, QA_SCALE_TOKEN, QA_SCALE_HEAD_TWO_PASS, QA_SCALE_HEAD_AMAX_ONLY, QA_SCALE_HEAD_GIVEN = 0, 1, 2, 3, 4
 QA_P_E4M3, QA_P_E4M3_HILO, QA_P_16BIT = 0, 1, 2
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 EXPORTED_SYMBOLS = (
     "qa_abi_version",
@@ -25,6 +25,7 @@ EXPORTED_SYMBOLS = (
     "qa_quantize_workspace_floats",
     "qa_quantize_fp8",
     "qa_fp8_attn_fwd",
+    "qa_merge_partials",
     "qa_last_launch_count",
 )
 
@@ -81,6 +82,9 @@ def load(build_if_missing: bool = True):
             ctypes.c_float, ctypes.c_int, vp,
         ]
         lib.qa_fp8_attn_fwd.restype = ctypes.c_int
+        lib.qa_merge_partials.argtypes = [vp, vp, vp, ctypes.c_int, vp, vp, ctypes.c_longlong, ctypes.c_int,
+                                          ctypes.c_int, vp]
+        lib.qa_merge_partials.restype = ctypes.c_int
         if lib.qa_abi_version() != ABI_VERSION:
             raise NativeError(f"ABI mismatch: library {lib.qa_abi_version()} != binding {ABI_VERSION}")
         _lib = lib
@@ -109,10 +113,13 @@ def last_launch_count() -> int:
     return int(load().qa_last_launch_count())
 
 
-def quantize_fp8(tensors: Sequence[torch.Tensor], scale_mode: int) -> Tuple[list, list]:
+def quantize_fp8(tensors: Sequence[torch.Tensor], scale_mode: int,
+                 scales: Optional[Sequence[torch.Tensor]] = None) -> Tuple[list, list]:
     """Quantise 1-3 CUDA tensors [B,H,S_i,D] (bf16/fp16, same B,H,D,dtype) in one launch pair.
 
     Returns ([e4m3 tensors], [fp32 scales: [B,H] head-wise or [B,H,S_i] token-wise]).
+    ``QA_SCALE_HEAD_AMAX_ONLY`` returns ([], scales) without quantising; ``QA_SCALE_HEAD_GIVEN`` quantises with the
+    fp32 [B,H] ``scales`` passed in.
     """
     lib = load()
     n = len(tensors)
@@ -126,8 +133,14 @@ def quantize_fp8(tensors: Sequence[torch.Tensor], scale_mode: int) -> Tuple[list
         if t.stride(3) != 1 or any(s % 8 for s in t.stride()[:3]) or t.data_ptr() % 16:
             t = t.contiguous()
         xs.append(t)
-    outs = [torch.empty(t.shape, dtype=torch.float8_e4m3fn, device=dev) for t in xs]
-    if scale_mode in (QA_SCALE_HEAD, QA_SCALE_HEAD_TWO_PASS):
+    amax_only = scale_mode == QA_SCALE_HEAD_AMAX_ONLY
+    outs = [] if amax_only else [torch.empty(t.shape, dtype=torch.float8_e4m3fn, device=dev) for t in xs]
+    if scale_mode == QA_SCALE_HEAD_GIVEN:
+        if scales is None or len(scales) != n:
+            raise ValueError("quantize_fp8: QA_SCALE_HEAD_GIVEN needs one [B,H] fp32 scale tensor per input")
+        scales = [s_.to(device=dev, dtype=torch.float32).reshape(B, H).contiguous() for s_ in scales]
+        ws_ptr = None
+    elif scale_mode in (QA_SCALE_HEAD, QA_SCALE_HEAD_TWO_PASS, QA_SCALE_HEAD_AMAX_ONLY):
         scales = [torch.empty((B, H), dtype=torch.float32, device=dev) for _ in xs]
         n_ws = int(lib.qa_quantize_workspace_floats(B, H, max(t.shape[2] for t in xs), D))
         ws = torch.empty((n_ws,), dtype=torch.float32, device=dev)
@@ -137,7 +150,7 @@ def quantize_fp8(tensors: Sequence[torch.Tensor], scale_mode: int) -> Tuple[list
         ws_ptr = None
     vp = ctypes.c_void_p
     x_arr = (vp * n)(*[t.data_ptr() for t in xs])
-    o_arr = (vp * n)(*[t.data_ptr() for t in outs])
+    o_arr = (vp * n)(*[t.data_ptr() for t in outs]) if outs else (vp * n)()
     s_arr = (vp * n)(*[t.data_ptr() for t in scales])
     strides = (ctypes.c_int64 * (4 * n))(*[s for t in xs for s in t.stride()])
     S = (ctypes.c_int * n)(*[t.shape[2] for t in xs])
@@ -192,3 +205,28 @@ def fp8_attn_fwd(q8: torch.Tensor, k8: torch.Tensor, v: torch.Tensor, scale_q: t
     global launch_total
     launch_total += int(lib.qa_last_launch_count())
     return (out, lse) if return_lse else out
+
+
+def merge_partials(o_acc: Optional[torch.Tensor], lse_acc: torch.Tensor, o_new: torch.Tensor, lse_new: torch.Tensor,
+                   *, first: bool, out: Optional[torch.Tensor] = None) -> None:
+    """(o_acc, lse_acc) <- combine with the partial result (o_new, lse_new) of one key block (include/qattn.h).
+
+    o_acc fp32 [..., D] / lse_acc fp32 [...]; o_new 16-bit, lse_new fp32.  With ``out`` (16-bit) the merged rows go
+    there instead of into o_acc (the last ring step)."""
+    lib = load()
+    D = o_new.shape[-1]
+    rows = o_new.numel() // D
+    for t in (o_acc, lse_acc, o_new, lse_new, out):
+        if t is not None and not t.is_contiguous():
+            raise ValueError("merge_partials: tensors must be contiguous")
+    if lse_acc.dtype != torch.float32 or lse_new.dtype != torch.float32 or (o_acc is not None and o_acc.dtype != torch.float32):
+        raise ValueError("merge_partials: accumulators and LSE must be fp32")
+    dev = o_new.device
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        rc = lib.qa_merge_partials(o_acc.data_ptr() if o_acc is not None else None, lse_acc.data_ptr(),
+                                   o_new.data_ptr(), _dt_code(o_new.dtype), lse_new.data_ptr(),
+                                   out.data_ptr() if out is not None else None, rows, D, int(bool(first)), stream)
+    _check(rc, "qa_merge_partials")
+    global launch_total
+    launch_total += int(lib.qa_last_launch_count())

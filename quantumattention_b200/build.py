@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libqattn_sm100.so")
 PROBE_PATH = os.path.join(HERE, "qa_probe")
-SOURCES = ["api.cu", "quantize.cu", "attn_fwd.cu"]
+SOURCES = ["api.cu", "quantize.cu", "merge.cu", "attn_fwd.cu"]
 HEADERS = ["ptx.cuh", "tma_host.h", "qattn_internal.h", os.path.join("..", "..", "include", "qattn.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -42,12 +42,28 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
     deps = srcs + [os.path.normpath(os.path.join(CSRC, h)) for h in HEADERS]
     if force or _stale(LIB_PATH, deps):
-        cmd = [_nvcc(), *NVCC_FLAGS, "--shared", "-o", LIB_PATH, *srcs]
+        compile_and_link(LIB_PATH, srcs, extra=["-Xptxas=-v"] if verbose else [], verbose=verbose)
+    return LIB_PATH
+
+
+def compile_and_link(out: str, srcs, extra=(), verbose: bool = False) -> None:
+    """One nvcc -c per translation unit, all at once (attn_fwd.cu dominates), then a link step."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    objdir = os.path.join(HERE, "build", os.path.basename(out) + ".d")
+    os.makedirs(objdir, exist_ok=True)
+    objs = [os.path.join(objdir, os.path.basename(s) + ".o") for s in srcs]
+
+    def one(pair):
+        src, obj = pair
+        cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-c", "-o", obj, src]
         if verbose:
-            cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), file=sys.stderr)
         subprocess.run(cmd, check=True)
-    return LIB_PATH
+
+    with ThreadPoolExecutor(max_workers=len(srcs)) as ex:
+        list(ex.map(one, zip(srcs, objs)))
+    subprocess.run([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-o", out, *objs], check=True)
 
 
 def build_probe(force: bool = False) -> str:

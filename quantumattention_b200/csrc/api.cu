@@ -76,22 +76,24 @@ int qa_quantize_fp8(int n_tensors, const void* const* x, int x_dtype, const int6
     if (x_dtype != QA_DT_BF16 && x_dtype != QA_DT_FP16)
         return set_error(QA_ERR_INVALID, "x_dtype must be bf16 or fp16");
     const bool two_pass = scale_mode == QA_SCALE_HEAD_TWO_PASS;
-    if (two_pass) scale_mode = QA_SCALE_HEAD;
+    const bool given = scale_mode == QA_SCALE_HEAD_GIVEN, amax_only = scale_mode == QA_SCALE_HEAD_AMAX_ONLY;
+    if (two_pass || given || amax_only) scale_mode = QA_SCALE_HEAD;
     if (scale_mode != QA_SCALE_HEAD && scale_mode != QA_SCALE_TOKEN)
         return set_error(QA_ERR_INVALID, "Unsupported scaling_method code: %d", scale_mode);
     if (D != 64 && D != 128 && D != 256) return set_error(QA_ERR_INVALID, "Unsupported head dimension: %d", D);
     if (B < 1 || H < 1 || int64_t(B) * H > 65535) return set_error(QA_ERR_INVALID, "B*H out of range");
-    if (scale_mode == QA_SCALE_HEAD && !amax_ws) return set_error(QA_ERR_INVALID, "amax_ws required for head-wise");
+    if (scale_mode == QA_SCALE_HEAD && !given && !amax_ws) return set_error(QA_ERR_INVALID, "amax_ws required for head-wise");
     QuantArgs a;
     memset(&a, 0, sizeof(a));
     for (int i = 0; i < n_tensors; ++i) {
-        if (!x[i] || !x8[i] || !scale[i]) return set_error(QA_ERR_INVALID, "null tensor pointer (tensor %d)", i);
+        if (!x[i] || (!x8[i] && !amax_only) || !scale[i])
+            return set_error(QA_ERR_INVALID, "null tensor pointer (tensor %d)", i);
         if (S[i] < 1) return set_error(QA_ERR_INVALID, "empty sequence (tensor %d)", i);
         const int64_t* st = x_strides + 4 * i;
         if (st[3] != 1) return set_error(QA_ERR_INVALID, "last-dim stride must be 1 (tensor %d)", i);
         if ((reinterpret_cast<uintptr_t>(x[i]) & 15) || (st[0] & 7) || (st[1] & 7) || (st[2] & 7))
             return set_error(QA_ERR_INVALID, "rows must be 16-byte aligned (tensor %d)", i);
-        if (reinterpret_cast<uintptr_t>(x8[i]) & 15) return set_error(QA_ERR_INVALID, "x8 must be 16-byte aligned");
+        if (!amax_only && (reinterpret_cast<uintptr_t>(x8[i]) & 15)) return set_error(QA_ERR_INVALID, "x8 must be 16-byte aligned");
         a.x[i] = x[i];
         a.x8[i] = x8[i];
         a.scale[i] = scale[i];
@@ -101,6 +103,8 @@ int qa_quantize_fp8(int n_tensors, const void* const* x, int x_dtype, const int6
     a.B = B, a.H = H, a.D = D;
     a.amax_ws = amax_ws;
     a.force_two_pass = two_pass ? 1 : 0;
+    a.given_scale = given ? 1 : 0;
+    a.amax_only = amax_only ? 1 : 0;
     int max_S = 0;
     for (int i = 0; i < n_tensors; ++i) max_S = S[i] > max_S ? S[i] : max_S;
     a.ws_floats = qa_quantize_workspace_floats(B, H, max_S, D);
@@ -152,6 +156,24 @@ int qa_fp8_attn_fwd(const void* q8, const void* k8, const void* v, int v_dtype, 
     a.v_dtype = v_dtype;
     a.out_dtype = out_dtype;
     return attn_fwd_dispatch(a, static_cast<cudaStream_t>(stream), &g_launches);
+}
+
+int qa_merge_partials(float* o_acc, float* lse_acc, const void* o_new, int o_dtype, const float* lse_new, void* out,
+                      long long rows, int D, int first, void* stream) {
+    g_launches = 0;
+    if (!lse_acc || !o_new || !lse_new) return set_error(QA_ERR_INVALID, "null pointer argument");
+    if (!o_acc && !(first && out)) return set_error(QA_ERR_INVALID, "o_acc may only be NULL when first != 0 and out is given");
+    if (o_dtype != QA_DT_BF16 && o_dtype != QA_DT_FP16) return set_error(QA_ERR_INVALID, "o_dtype must be bf16 or fp16");
+    if (D != 64 && D != 128 && D != 256) return set_error(QA_ERR_INVALID, "Unsupported head dimension: %d", D);
+    if (rows < 1) return set_error(QA_ERR_INVALID, "empty problem");
+    if ((reinterpret_cast<uintptr_t>(o_acc) | reinterpret_cast<uintptr_t>(o_new) | reinterpret_cast<uintptr_t>(out)) & 15)
+        return set_error(QA_ERR_INVALID, "tensor base pointers must be 16-byte aligned");
+    int rc = check_device();
+    if (rc != QA_OK) return rc;
+    MergeArgs a;
+    a.o_acc = o_acc, a.lse_acc = lse_acc, a.o_new = o_new, a.lse_new = lse_new, a.out = out;
+    a.rows = rows, a.D = D, a.dtype = o_dtype, a.first = first ? 1 : 0;
+    return merge_dispatch(a, static_cast<cudaStream_t>(stream), &g_launches);
 }
 
 }  // extern "C"

@@ -16,6 +16,8 @@ struct QuantArgs {
     float* amax_ws;
     int rows_per_cta;
     int force_two_pass;
+    int given_scale;  // QA_SCALE_HEAD_GIVEN: scale[] is an input
+    int amax_only;    // QA_SCALE_HEAD_AMAX_ONLY: write scale[] only
     size_t ws_floats;
 };
 
@@ -37,10 +39,23 @@ struct AttnArgs {
     int out_dtype;
 };
 
+struct MergeArgs {
+    float* o_acc;
+    float* lse_acc;
+    const void* o_new;
+    const float* lse_new;
+    void* out;
+    long long rows;
+    int D;
+    int dtype;
+    int first;
+};
+
 int set_error(int code, const char* fmt, ...);
 int set_cuda_error(const char* what, cudaError_t e);
 
 int quantize_dispatch(QuantArgs& a, int x_dtype, int scale_mode, int n_tensors, cudaStream_t stream, int* launches);
 int attn_fwd_dispatch(const AttnArgs& a, cudaStream_t stream, int* launches);
+int merge_dispatch(const MergeArgs& a, cudaStream_t stream, int* launches);
 
 }  // namespace qa

@@ -2,7 +2,13 @@
 # scripts/build_variant.sh NAME [extra nvcc flags...]  -> quantumattention_b200/libqattn_sm100_NAME.so  (dev A/B builds)
 set -e
 name=$1; shift
-cd "$(dirname "$0")/../quantumattention_b200/csrc"
-nvcc -gencode arch=compute_100a,code=sm_100a -std=c++17 -O3 -lineinfo -Xcompiler -fPIC "$@" --shared \
-  -o ../libqattn_sm100_$name.so api.cu quantize.cu attn_fwd.cu
-echo built ../libqattn_sm100_$name.so
+cd "$(dirname "$0")/.."
+python - "$name" "$@" <<'PY'
+import sys
+from quantumattention_b200 import build as b
+import os
+name, extra = sys.argv[1], sys.argv[2:]
+out = os.path.join(b.HERE, f"libqattn_sm100_{name}.so")
+b.compile_and_link(out, [os.path.join(b.CSRC, s) for s in b.SOURCES], extra=extra)
+print("built", out)
+PY
