@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """bench.py - FP8 attention forward throughput on B200 (the metric of BASELINE.json).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C2_flux|C3_llama|C1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload C2_flux|C3_llama|C1|C4_video]
 
 One "step" = one call of the public entry point ``quantum_attn.fp8_attn_func(q, k, v)`` on 16-bit inputs that are
 already resident in HBM: dynamic FP8 quantisation of Q/K/V plus the fused attention kernel - the same thing the
@@ -9,7 +10,9 @@ reference's own benchmark times (tests/test_interface.py:90-139).  FLOPs are the
 (halved when causal, tests/test_interface.py:121-125).
 
 Multi-GPU (torchrun, one rank per GPU): the path shards by batch x head with no collective, so every rank runs its
-own batch element of the same workload (weak scaling); the time is the max over ranks.
+own batch element of the same workload (weak scaling); the time is the max over ranks.  The long-video workload
+(C4_video) instead shards ONE sequence over the ranks and runs the e4m3 K/V ring of quantumattention_b200/parallel.py
+(NCCL send/recv overlapped with the kernel; strong scaling).
 
 ``--impl reference`` times the reference's op definition (src/quantum_attn/ops.py:64-95: dequantise, aten SDPA) on the
 box's host cores - the reference has no CPU kernel and its only GPU kernel is an sm_90a cubin that cannot load on
@@ -34,6 +37,8 @@ WORKLOADS = {
     "C1": (2, 8, 512, 64, True),
     "C2_flux": (1, 24, 4608, 128, False),
     "C3_llama": (1, 32, 8192, 128, True),
+    # BASELINE.json configs[3]: Wan-720p token count; one GPU runs it whole, N GPUs run the sequence ring (strong scaling)
+    "C4_video": (1, 24, 75600, 128, False),
 }
 METRIC = "fp8_attn_fwd_tflops"
 UNIT = "TFLOP/s"
@@ -117,7 +122,8 @@ def cpu_reference_leg(workload, budget_s=12.0):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     hs = 1 if S >= 8192 else min(H, 2)  # MATH materialises S x S per head: keep the sample bounded
-    q, k, v = oracle.make_qkv(1, hs, S, S, D, seed=0)
+    rows = S if S <= 16384 else 2048    # ... and for the video shape only a slab of query rows of that head
+    q, k, v = oracle.make_qkv(1, hs, rows, S, D, seed=0)
     q8b, sq = oracle.quantize_fp8(q.float().numpy(), "head-wise")
     k8b, sk = oracle.quantize_fp8(k.float().numpy(), "head-wise")
     q8 = torch.from_numpy(q8b).view(torch.float8_e4m3fn)
@@ -131,10 +137,11 @@ def cpu_reference_leg(workload, budget_s=12.0):
         oracle.cpu_reference_step(q8, k8, vf, sq, sk, is_causal=causal)
         times.append(time.perf_counter() - t0)
     t = statistics.median(times)
-    tflops = flops_of(1, hs, S, D, causal) / t / 1e12
+    tflops = flops_of(1, hs, S, D, causal) * (rows / S) / t / 1e12
     return {
         "value": tflops, "unit": UNIT, "cores": cores, "kind": "port",
-        "sample": f"{hs} of {B * H} heads of {workload} (S={S}, D={D}, causal={causal}), fp32 aten SDPA MATH on the "
+        "sample": f"{hs} of {B * H} heads of {workload} (S={S}, D={D}, causal={causal}"
+                  + (f", {rows} of {S} query rows" if rows != S else "") + "), fp32 aten SDPA MATH on the "
                   f"dequantised inputs, median of {len(times)} runs; whole-workload time extrapolates linearly in heads",
         "seconds_per_sample": t,
     }
@@ -165,7 +172,7 @@ def fp8_gemm_peak(device):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2_flux", choices=sorted(WORKLOADS))
@@ -179,11 +186,22 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     B, H, S, D, causal = WORKLOADS[args.workload]
+    ring = args.workload == "C4_video" and world > 1
+    if args.steps is None:
+        args.steps = 1000 if S <= 16384 else 30
+    if S > 16384:
+        args.e2e_steps = min(args.e2e_steps, 10)
     config = {
         "workload": f"{args.workload}: B={B} (per GPU) H={H} S={S} D={D} causal={causal}, head-wise FP8 scales",
         "per_gpu_batch": B, "heads": H, "seq_len": S, "head_dim": D, "causal": causal,
         "parallelism": f"batch x head sharding over {world} GPU(s), no collective",
     }
+    if ring:
+        if S % world:
+            raise SystemExit(f"bench.py: S={S} does not split over {world} ranks")
+        config["workload"] = (f"{args.workload}: ONE problem B={B} H={H} S={S} D={D} causal={causal} over {world} GPUs, "
+                              f"{S // world} tokens per rank, head-wise FP8 scales (global via all_reduce MAX)")
+        config["parallelism"] = f"sequence ring over {world} GPUs: e4m3 K/V blocks by NCCL send/recv, (O, LSE) merge"
 
     # ------------------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
@@ -221,20 +239,30 @@ def main():
     _native.load(build_if_missing=False)
 
     # rotating input sets so the working set (> 126 MB L2) is not L2-resident between steps
-    bytes_per_set = 3 * B * H * S * D * 2
+    bytes_per_set = 3 * B * H * (S // world if ring else S) * D * 2
     n_sets = max(2, math.ceil(300e6 / bytes_per_set))
     import oracle
 
+    S_loc = S // world if ring else S
     sets = []
     for i in range(n_sets):
-        q, k, v = oracle.make_qkv(B, H, S, S, D, seed=1000 * rank + i)
+        if ring:  # every rank generates the same sequence and keeps its slice
+            q, k, v = (t[:, :, rank * S_loc:(rank + 1) * S_loc].contiguous() for t in oracle.make_qkv(B, H, S, S, D, seed=i))
+        else:
+            q, k, v = oracle.make_qkv(B, H, S, S, D, seed=1000 * rank + i)
         sets.append((q.to(dev), k.to(dev), v.to(dev)))
     config["l2_policy"] = f"rotating {n_sets} input sets ({n_sets * bytes_per_set / 1e6:.0f} MB > 126 MB L2)"
     config["pv_mode"] = pv_mode
 
-    def step(i):
-        q, k, v = sets[i % n_sets]
+    from quantumattention_b200 import parallel
+
+    def attn_call(q, k, v):
+        if ring:
+            return parallel.ring_fp8_attention(q, k, v)
         return quantum_attn.fp8_attn_func(q, k, v, is_causal=causal)
+
+    def step(i):
+        return attn_call(*sets[i % n_sets])
 
     def barrier():
         if dist is not None:
@@ -268,7 +296,8 @@ def main():
         total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
     fl = flops_of(B, H, S, D, causal)
-    value = world * fl / (ms_per_step * 1e-3) / 1e12
+    job_fl = fl if ring else world * fl  # the ring splits ONE problem; head/batch sharding replicates the workload
+    value = job_fl / (ms_per_step * 1e-3) / 1e12
 
     # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region.
     # Every step copies its own q, k, v from pinned host memory and reads its own output back.  The three legs run on
@@ -298,7 +327,7 @@ def main():
             s_main.wait_event(up[b_])
             if down[b_] is not None:
                 s_main.wait_event(down[b_])  # outs[b_] of two steps ago has been read back
-            outs[b_] = quantum_attn.fp8_attn_func(*dbuf[b_], is_causal=causal)
+            outs[b_] = attn_call(*dbuf[b_])
             done[b_] = torch.cuda.Event()
             done[b_].record(s_main)
             with torch.cuda.stream(s_out):
@@ -323,7 +352,7 @@ def main():
         t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
-    e2e_value = world * fl / (e2e_ms / args.e2e_steps * 1e-3) / 1e12
+    e2e_value = job_fl / (e2e_ms / args.e2e_steps * 1e-3) / 1e12
 
     # ---- the quantiser alone (HBM-bound leg of the step): Q, K, V of one input set per launch, rotating sets
     quant_ms = None
@@ -338,17 +367,20 @@ def main():
         torch.cuda.synchronize()
         qev, _native.quant_events = _native.quant_events, None
         quant_ms = statistics.mean(a.elapsed_time(b) for a, b in qev)  # memset + kernel, per call, on the stream
-        # host-side cost of one step (python + ctypes + allocator), GPU not waited for
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for i in range(50):
-            step(i)
-        host_us = (time.perf_counter() - t0) / 50 * 1e6
-        torch.cuda.synchronize()
+        # host-side cost of one step (python + ctypes + allocator), GPU not waited for (not in ring mode: a step
+        # there holds collectives and every rank would have to take part)
+        host_us = None
+        if not ring:
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for i in range(50):
+                step(i)
+            host_us = (time.perf_counter() - t0) / 50 * 1e6
+            torch.cuda.synchronize()
 
     # ---- the other two P modes, kernel only (context for the headline mode; 20 launches each)
     other_modes = {}
-    if rank == 0 and not args.no_other_modes:
+    if rank == 0 and not args.no_other_modes and not ring:
         for mode in ("fp8", "fp8_hilo", "16bit"):
             if mode == pv_mode:
                 continue
@@ -369,7 +401,8 @@ def main():
 
     peaks = load_peaks()
     fp8_meas = fp8_gemm_peak(dev)
-    achieved = fl / (attn_ms * 1e-3) / 1e12
+    launch_fl = fl // (world * world) if ring else fl  # a ring step attends S/N queries to S/N keys
+    achieved = launch_fl / (attn_ms * 1e-3) / 1e12
     # The driver measures bf16 only; kind::f8f6f4 runs at exactly twice the bf16 rate on the same datapath, so the
     # FP8 denominator is 2 x the MEASURED bf16 GEMM burst figure.  Spec and measured-FP8-GEMM fractions sit beside it.
     peak = 2.0 * peaks["bf16_tflops"]
@@ -388,28 +421,28 @@ def main():
         "frac_of_fp8_spec_4500": achieved / FP8_SPEC_TFLOPS,
         "fp8_gemm_tflops_measured_here": fp8_meas,
         "frac_of_measured_fp8_gemm": (achieved / fp8_meas) if fp8_meas else None,
-        "attn_kernel_ms": attn_ms, "flops_per_launch": fl,
+        "attn_kernel_ms": attn_ms, "flops_per_launch": launch_fl,
         "exp_bound_tflops_at_max_clock": 148 * 16 * 1.965e9 * 4 * D / 1e12,
     }
-    quant_bytes = 3 * B * H * S * D * 3 + 3 * B * H * 4  # 2 B in + 1 B out per element, + scales
+    quant_bytes = 3 * B * H * S_loc * D * 3 + 3 * B * H * 4  # 2 B in + 1 B out per element, + scales
     quantiser = {
-        "kernel": "quant_head_fused_kernel (+ workspace memset)", "bound": "hbm", "ms": quant_ms,
+        "kernel": "quant_head_ring_kernel (+ workspace memset)", "bound": "hbm", "ms": quant_ms,
         "achieved": quant_bytes / (quant_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
         "frac": quant_bytes / (quant_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes": quant_bytes,
         "traffic": None,
     }
     try:
         tq = json.load(open(tpath)).get("quantiser", {})
-        quantiser["traffic"] = tq.get("quant_head_fused_kernel")
+        quantiser["traffic"] = tq.get("quant_head_ring_kernel")
     except Exception:
         pass
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if ring else "weak", "vs_baseline": None,
         "dtype": "fp8_e4m3" if pv_mode != "16bit" else "fp8_e4m3(QK)+bf16(PV)", "data": "synthetic",
         "config": config, "clocks": clocks, "gpu_launches": launches,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 3 * B * H * S * D * 2,
-                "d2h_bytes_per_step": B * H * S * D * 2, "ms_per_step": e2e_ms / args.e2e_steps},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 3 * B * H * S_loc * D * 2,
+                "d2h_bytes_per_step": B * H * S_loc * D * 2, "ms_per_step": e2e_ms / args.e2e_steps},
         "roofline": roofline,
         "quantiser": quantiser,
         "host_us_per_step": host_us,

@@ -134,11 +134,15 @@ def _nccl_ring_worker(rank, world, port, tmp):
         S = S_local * world
         q, k, v = oracle.make_qkv(B, H, S, S, D, seed=9)
         sl = slice(rank * S_local, (rank + 1) * S_local)
-        out = parallel.ring_fp8_attention(q[:, :, sl].contiguous().cuda(), k[:, :, sl].contiguous().cuda(),
-                                          v[:, :, sl].contiguous().cuda())
-        whole = quantum_attn.fp8_attn_func(q.cuda(), k.cuda(), v.cuda())[:, :, sl]
-        torch.cuda.synchronize()
-        torch.save({"ring": out.cpu(), "whole": whole.cpu()}, os.path.join(tmp, f"r{rank}.pt"))
+        res = {}
+        for pv in ("fp8", "fp8_hilo"):
+            out = parallel.ring_fp8_attention(q[:, :, sl].contiguous().cuda(), k[:, :, sl].contiguous().cuda(),
+                                              v[:, :, sl].contiguous().cuda(), pv_mode=pv)
+            with quantum_attn.config.patch({"attention.pv_mode": pv}):
+                whole = quantum_attn.fp8_attn_func(q.cuda(), k.cuda(), v.cuda())[:, :, sl]
+            torch.cuda.synchronize()
+            res[pv] = (out.cpu(), whole.cpu())
+        torch.save(res, os.path.join(tmp, f"r{rank}.pt"))
     finally:
         dist.destroy_process_group()
 
@@ -152,6 +156,10 @@ def test_nccl_ring_matches_unsharded_kernel(tmp_path):
     mp.spawn(_nccl_ring_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     for r in range(world):
         d = torch.load(os.path.join(tmp_path, f"r{r}.pt"))
-        m = oracle.compare(d["ring"].float().numpy(), d["whole"].float().numpy())
-        # same quantised bytes on both paths; the difference is the fp32 merge + one extra bf16 rounding of partials
-        assert m["cos_sim"] > 0.9999 and m["max_abs_over_row_rms"] < 0.3, m
+        # Same quantised Q/K/V bytes on both paths.  P is rounded to e4m3 relative to a running maximum that depends on
+        # the key-block partition, so two "fp8" results differ by two independent P roundings; with hi+lo P the
+        # difference collapses to the bf16 rounding of the partial results.
+        m = oracle.compare(d["fp8"][0].float().numpy(), d["fp8"][1].float().numpy())
+        assert m["cos_sim"] > 0.999 and m["max_abs_over_row_rms"] < 0.4, m
+        m = oracle.compare(d["fp8_hilo"][0].float().numpy(), d["fp8_hilo"][1].float().numpy())
+        assert m["cos_sim"] > 0.99999 and m["max_abs_over_row_rms"] < 0.03, m
