@@ -393,6 +393,15 @@ def main():
                 torch.cuda.synchronize()
                 ev, _native.attn_events = _native.attn_events, None
                 other_modes[mode] = fl / (statistics.mean(a.elapsed_time(b) for a, b in ev) * 1e-3) / 1e12
+        # the 16-bit entry point (`attn_func`: bf16 Q / K / V, kind::f16 MMAs, no quantiser), same shape and FLOP count
+        for i in range(3):
+            quantum_attn.attn_func(*sets[i % n_sets], is_causal=causal)
+        _native.attn_events = []
+        for i in range(20):
+            quantum_attn.attn_func(*sets[i % n_sets], is_causal=causal)
+        torch.cuda.synchronize()
+        ev, _native.attn_events = _native.attn_events, None
+        other_modes["attn_func_bf16"] = fl / (statistics.mean(a.elapsed_time(b) for a, b in ev) * 1e-3) / 1e12
 
     if rank != 0:
         if dist is not None:

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define QA_ABI_VERSION 2
+#define QA_ABI_VERSION 3
 
 /* element types */
 #define QA_DT_BF16 0
@@ -101,6 +101,20 @@ int qa_fp8_attn_fwd(const void* q8, const void* k8, const void* v, int v_dtype, 
                     const float* scale_k, const float* scale_v, int scale_mode, void* out, int out_dtype, float* lse,
                     int B, int Hq, int Hkv, int Sq, int Skv, int D, int causal, float sm_scale, int p_mode,
                     void* stream);
+
+/* The same fused forward with Q and K left in 16 bits: S = Q K^T as tcgen05 kind::f16, P and V 16-bit, fp32
+ * accumulation and softmax.  Replaces the reference's non-FP8 TK module - `attention_forward(q, k, v, causal)`
+ * (src/quantum_attn/tk/attention.py:355-360 with is_fp8 = false, kernel :238-240,289-313) - behind `attn_func`
+ * (src/quantum_attn/quantum_attn_interface.py:41-59) / op `quantum_attn::attention_forward`
+ * (src/quantum_attn/ops.py:32-45):
+ *     out = softmax(sm_scale * q k^T  [+ top-left causal mask]) v
+ *
+ *   q, k, v     dense [B,Hq,Sq,D], [B,Hkv,Skv,D], [B,Hkv,Skv,D], all of `dtype` (QA_DT_BF16 / QA_DT_FP16)
+ *   out         dense [B,Hq,Sq,D] of `dtype`;  lse as in qa_fp8_attn_fwd (NULL to skip)
+ *   Hq % Hkv == 0; D in {64, 128, 256}; causal mask is top-left aligned.
+ */
+int qa_attn_fwd(const void* q, const void* k, const void* v, int dtype, void* out, float* lse, int B, int Hq, int Hkv,
+                int Sq, int Skv, int D, int causal, float sm_scale, void* stream);
 
 /* Combine two partial attention results over disjoint key sets, row by row:
  *     m = max(lse_acc, lse_new); w_x = exp(lse_x - m); O = (w_acc O_acc + w_new O_new) / (w_acc + w_new);

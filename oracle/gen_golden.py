@@ -90,6 +90,28 @@ def main():
             out_ref_fp32=out_fp32.numpy(),
             causal=np.array(causal),
         )
+    # ---- 16-bit attention vectors: the reference's `_attention_forward` (src/quantum_attn/ops.py:15-28) on CPU, in the
+    # input dtype (its arithmetic) and on the fp32-widened tensors.  Own generator: the files above stay byte-identical.
+    g16 = torch.Generator(device="cpu").manual_seed(4321)
+    for name, (B, Hq, Hkv, Sq, Skv, D, causal, dtype) in {
+        "attn16_d64_causal": (1, 2, 2, 200, 200, 64, True, torch.bfloat16),
+        "attn16_d128": (1, 2, 2, 130, 257, 128, False, torch.bfloat16),
+        "attn16_d128_fp16_causal": (2, 2, 2, 300, 300, 128, True, torch.float16),
+        "attn16_d256_causal": (1, 1, 1, 160, 160, 256, True, torch.bfloat16),
+    }.items():
+        q = torch.randn(B, Hq, Sq, D, generator=g16).to(dtype)
+        k = torch.randn(B, Hkv, Skv, D, generator=g16).to(dtype)
+        v = torch.randn(B, Hkv, Skv, D, generator=g16).to(dtype)
+        out_16 = ref_ops._attention_forward(q, k, v, is_causal=causal)
+        out_fp32 = ref_ops._attention_forward(q.float(), k.float(), v.float(), is_causal=causal)
+        np.savez_compressed(
+            os.path.join(OUT, f"{name}.npz"),
+            q_bits=bf16_bits(q), k_bits=bf16_bits(k), v_bits=bf16_bits(v),  # int16 views (bf16 or fp16 bit patterns)
+            fp16=np.array(dtype == torch.float16),
+            out_ref_16_bits=bf16_bits(out_16),
+            out_ref_fp32=out_fp32.numpy(),
+            causal=np.array(causal),
+        )
     print("golden vectors written to", os.path.normpath(OUT))
 
 

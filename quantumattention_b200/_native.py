@@ -16,7 +16,7 @@ from . import build as _build
 QA_DT_BF16, QA_DT_FP16, QA_DT_E4M3 = 0, 1, 2
 QA_SCALE_HEAD, QA_SCALE_TOKEN, QA_SCALE_HEAD_TWO_PASS, QA_SCALE_HEAD_AMAX_ONLY, QA_SCALE_HEAD_GIVEN = 0, 1, 2, 3, 4
 QA_P_E4M3, QA_P_E4M3_HILO, QA_P_16BIT = 0, 1, 2
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 EXPORTED_SYMBOLS = (
     "qa_abi_version",
@@ -25,6 +25,7 @@ EXPORTED_SYMBOLS = (
     "qa_quantize_workspace_floats",
     "qa_quantize_fp8",
     "qa_fp8_attn_fwd",
+    "qa_attn_fwd",
     "qa_merge_partials",
     "qa_last_launch_count",
 )
@@ -82,6 +83,8 @@ def load(build_if_missing: bool = True):
             ctypes.c_float, ctypes.c_int, vp,
         ]
         lib.qa_fp8_attn_fwd.restype = ctypes.c_int
+        lib.qa_attn_fwd.argtypes = [vp, vp, vp, ctypes.c_int, vp, vp] + [ctypes.c_int] * 7 + [ctypes.c_float, vp]
+        lib.qa_attn_fwd.restype = ctypes.c_int
         lib.qa_merge_partials.argtypes = [vp, vp, vp, ctypes.c_int, vp, vp, ctypes.c_longlong, ctypes.c_int,
                                           ctypes.c_int, vp]
         lib.qa_merge_partials.restype = ctypes.c_int
@@ -202,6 +205,33 @@ def fp8_attn_fwd(q8: torch.Tensor, k8: torch.Tensor, v: torch.Tensor, scale_q: t
             ev1.record(tstream)
             attn_events.append((ev0, ev1))
     _check(rc, "qa_fp8_attn_fwd")
+    global launch_total
+    launch_total += int(lib.qa_last_launch_count())
+    return (out, lse) if return_lse else out
+
+
+def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, is_causal: bool, sm_scale: float,
+             return_lse: bool = False):
+    """Launch the fused forward kernel on 16-bit q, k, v (all bf16 or all fp16), dense [B,H,S,D]."""
+    lib = load()
+    B, Hq, Sq, D = q.shape
+    Hkv, Skv = k.shape[1], k.shape[2]
+    dev = q.device
+    q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+    out = torch.empty((B, Hq, Sq, D), dtype=q.dtype, device=dev)
+    lse = torch.empty((B, Hq, Sq), dtype=torch.float32, device=dev) if return_lse else None
+    with torch.cuda.device(dev):
+        tstream = torch.cuda.current_stream(dev)
+        if attn_events is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(tstream)
+        rc = lib.qa_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), _dt_code(q.dtype), out.data_ptr(),
+                             lse.data_ptr() if lse is not None else None, B, Hq, Hkv, Sq, Skv, D,
+                             int(bool(is_causal)), float(sm_scale), tstream.cuda_stream)
+        if attn_events is not None:
+            ev1.record(tstream)
+            attn_events.append((ev0, ev1))
+    _check(rc, "qa_attn_fwd")
     global launch_total
     launch_total += int(lib.qa_last_launch_count())
     return (out, lse) if return_lse else out

@@ -15,8 +15,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libqattn_sm100.so")
 PROBE_PATH = os.path.join(HERE, "qa_probe")
-SOURCES = ["api.cu", "quantize.cu", "merge.cu", "attn_fwd.cu"]
-HEADERS = ["ptx.cuh", "tma_host.h", "qattn_internal.h", os.path.join("..", "..", "include", "qattn.h")]
+SOURCES = ["api.cu", "quantize.cu", "merge.cu", "attn_fwd.cu", "attn_fwd16.cu"]
+HEADERS = ["attn_fwd_kernel.cuh", "ptx.cuh", "tma_host.h", "qattn_internal.h", os.path.join("..", "..", "include", "qattn.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-std=c++17", "-O3", "-lineinfo",

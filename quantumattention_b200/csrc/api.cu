@@ -155,7 +155,38 @@ int qa_fp8_attn_fwd(const void* q8, const void* k8, const void* v, int v_dtype, 
     a.p_mode = p_mode;
     a.v_dtype = v_dtype;
     a.out_dtype = out_dtype;
+    a.qk_dtype = QA_DT_E4M3;
     return attn_fwd_dispatch(a, static_cast<cudaStream_t>(stream), &g_launches);
+}
+
+int qa_attn_fwd(const void* q, const void* k, const void* v, int dtype, void* out, float* lse, int B, int Hq, int Hkv,
+                int Sq, int Skv, int D, int causal, float sm_scale, void* stream) {
+    g_launches = 0;
+    if (!q || !k || !v || !out) return set_error(QA_ERR_INVALID, "null pointer argument");
+    if (dtype != QA_DT_BF16 && dtype != QA_DT_FP16)
+        return set_error(QA_ERR_INVALID, "Expected query, key, and value to have dtype fp16 or bf16 (code %d)", dtype);
+    if (D != 64 && D != 128 && D != 256) return set_error(QA_ERR_INVALID, "Unsupported head dimension: %d", D);
+    if (B < 1 || Hq < 1 || Hkv < 1 || Sq < 1 || Skv < 1) return set_error(QA_ERR_INVALID, "empty problem");
+    if (Hq % Hkv != 0)
+        return set_error(QA_ERR_INVALID, "Expect Hq to be a multiple of Hkv but got Hq=%d and Hkv=%d.", Hq, Hkv);
+    if (Hq > 65535 || B > 65535) return set_error(QA_ERR_INVALID, "B or Hq exceeds the grid limit 65535");
+    if (!(sm_scale > 0.f) || !(sm_scale < 1e30f)) return set_error(QA_ERR_INVALID, "sm_scale must be positive");
+    if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
+         reinterpret_cast<uintptr_t>(out)) & 15)
+        return set_error(QA_ERR_INVALID, "tensor base pointers must be 16-byte aligned");
+    int rc = check_device();
+    if (rc != QA_OK) return rc;
+    AttnArgs a;
+    a.q8 = q, a.k8 = k, a.v = v;
+    a.scale_q = a.scale_k = a.scale_v = nullptr;
+    a.out = out, a.lse = lse;
+    a.B = B, a.Hq = Hq, a.Hkv = Hkv, a.Sq = Sq, a.Skv = Skv, a.D = D;
+    a.causal = causal ? 1 : 0;
+    a.sm_scale = sm_scale;
+    a.scale_mode = QA_SCALE_HEAD;
+    a.p_mode = QA_P_16BIT;
+    a.v_dtype = a.out_dtype = a.qk_dtype = dtype;
+    return attn16_fwd_dispatch(a, static_cast<cudaStream_t>(stream), &g_launches);
 }
 
 int qa_merge_partials(float* o_acc, float* lse_acc, const void* o_new, int o_dtype, const float* lse_new, void* out,

@@ -1,0 +1,760 @@
+// Fused FP8 attention forward for sm_100a:  S = Q K^T (tcgen05 kind::f8f6f4, fp32 in TMEM)  ->  online softmax in
+// registers (one thread per query row, base-2 domain, lazy rescale)  ->  P written back into TMEM as e4m3  ->
+// O += P V (tcgen05, A operand from TMEM, V straight from its [kv][D] layout as an MN-major B operand).
+//
+// What it replaces: `fwd_attend_ker` of the reference (src/quantum_attn/tk/attention.py:97-349) and its launcher
+// (:355-647).  Same function (dequant scale folded into the exp2 argument as in :204-210,248-250; top-left causal
+// mask as in :252-263; ragged tails via TMA zero fill + -inf columns as in :269-271), different machine:
+//
+//   CTA = 2 query tiles of 128 rows, 12 warps (3 warpgroups; setmaxnreg moves registers to the softmax warps):
+//     warps 0-3  softmax + (rare) O rescale + epilogue of query tile 0   (thread r <-> TMEM lane r <-> query row r)
+//     warps 4-7  the same for query tile 1
+//     warp  8/10 MMA issuer of query tile 0 / 1 (one elected thread each)
+//     warp  9    TMA producer: Q once, K/V tiles of 128 keys through mbarrier rings      (warp 11 idle)
+//   The softmax / MMA hand-off runs in STEPS of 64 keys.  Per query tile TMEM holds ONE score buffer S and TWO
+//   P buffers: a softmax thread pulls its S_j row into registers and releases the buffer at once (s_free), so
+//   QK_{j+1} runs under the exponentials of step j; P_j goes to its own buffer, so PV_j never blocks a QK.
+//   Inside a softmax warp the step is software-pipelined: the load of S_{j+1} and its row maximum are
+//   interleaved with the last exponentials of step j, so a warp issues MUFU work almost without gaps.  That
+//   matters because at D = 128 the exp unit (MUFU, 16 / clk / SM), not the tensor pipe, bounds FP8 attention.
+//   To go past that bound a compile-time fraction of the exponentials is evaluated on the FMA pipe
+//   (Cody-Waite split + minimax polynomial, packed fp32x2 arithmetic) instead of MUFU.EX2.
+//   TMEM (512 columns): S_t at t*128 | P(t,b) at t*128 + 64 + b*32 | O_t at 256 + t*128.
+//   K and V tiles are shared by both query tiles, halving L2->SMEM traffic per FLOP.
+//
+// Deliberately absent: any non-sm_100 path, any fallback.
+#pragma once
+#include <cmath>
+#include <type_traits>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include "ptx.cuh"
+#include "qattn_internal.h"
+#include "tma_host.h"
+
+namespace qa {
+
+#ifdef QA_TRACE
+extern long long* g_trace_ptr;
+extern int g_trace_x, g_trace_y;
+#define QA_STAMP(role, step, ev)                                                                   \
+    do {                                                                                          \
+        if (p.trace && blockIdx.x == p.trace_x && blockIdx.y == p.trace_y && blockIdx.z == 0 && lane == 0 && (step) < 80) \
+            p.trace[((role) * 80 + (step)) * 8 + (ev)] = clock64();                               \
+    } while (0)
+#else
+#define QA_STAMP(role, step, ev) do { } while (0)
+#endif
+
+constexpr int BM = 128;  // query rows per tile (= TMEM lanes)
+constexpr int BN = 128;  // keys per K/V shared-memory tile (one TMA box)
+constexpr int BS = 64;   // keys per softmax / MMA step (half a tile)
+constexpr float kLog2e = 1.4426950408889634f;
+
+#ifndef QA_POLY_NUM
+#define QA_POLY_NUM 2  // of every 8 pairs of exponentials, how many run on the FMA pipe instead of MUFU
+#endif
+#ifndef QA_LOADQ
+#define QA_LOADQ 12    // S_{j+1} is pulled into registers after this many (of 16) quads of step j's exponentials
+#endif
+
+// QK16_: Q and K stay 16-bit (bf16 / fp16) and QK^T runs as kind::f16 - the reference's `attn_func` path
+// (src/quantum_attn/tk/attention.py:238-240,289-313); it implies the 16-bit P mode and has no dequantisation scales.
+template <int D_, int PMODE_, bool QK16_ = false>
+struct AttnCfg {
+    static constexpr int D = D_;
+    static constexpr int PMODE = PMODE_;
+    static constexpr bool QK16 = QK16_;
+    static constexpr bool V16 = (PMODE_ == QA_P_16BIT);
+    static_assert(!QK16_ || V16, "16-bit Q/K go with 16-bit P and V");
+    static constexpr int NQ = (D_ <= 128) ? 2 : 1;  // O for two tiles does not fit TMEM at D = 256
+    static constexpr int VB = V16 ? 2 : 1;          // bytes per V element
+    static constexpr int QB = QK16_ ? 2 : 1;        // bytes per Q / K element
+    // shared-memory tiles are stored as "boxes" whose rows are one swizzle span (<= 128 bytes) wide
+    static constexpr int QK_ROW = (D_ * QB) < 128 ? (D_ * QB) : 128;  // bytes per box row for Q / K
+    static constexpr int QK_BOXES = D_ * QB / QK_ROW;
+    static constexpr int QK_BOX_BYTES = QK_ROW * 128;
+    static constexpr int V_ROW = (D_ * VB) < 128 ? (D_ * VB) : 128;
+    static constexpr int V_BOXES = D_ * VB / V_ROW;
+    static constexpr int V_BOX_BYTES = V_ROW * BN;
+    static constexpr int Q_TILE = BM * D_ * QB;
+    static constexpr int K_TILE = BN * D_ * QB;
+    static constexpr int V_TILE = BN * D_ * VB;
+    static constexpr int O_BOXES = D_ / 64;  // 16-bit output, 64 elements = 128 bytes per box row
+    static constexpr int O_TILE = BM * D_ * 2;
+    static constexpr int STAGES = QK16_ ? (D_ == 64 ? 4 : (D_ == 128 ? 2 : 1))
+                                        : ((D_ == 64) ? 4 : (D_ == 128 ? (V16 ? 2 : 3) : 2));
+    static constexpr int SMEM_Q = 0;
+    static constexpr int SMEM_K = SMEM_Q + NQ * Q_TILE;
+    static constexpr int SMEM_V = SMEM_K + STAGES * K_TILE;
+    // O staging for the TMA store: its own region when two query tiles finish at different times; with a single
+    // tile (D = 256) every MMA has retired before the epilogue, so the dead K ring is reused
+    // with 16-bit Q a query tile is as large as its output tile and dead once the tile's last MMA has retired (which
+    // the epilogue waits for anyway): O is staged over Q
+    static constexpr int SMEM_O = QK16_ ? SMEM_Q : ((NQ == 2) ? SMEM_V + STAGES * V_TILE : SMEM_K);
+    static constexpr int SMEM_BAR = (NQ == 2 && !QK16_) ? SMEM_O + NQ * O_TILE : SMEM_V + STAGES * V_TILE;
+    static_assert(QK16_ || NQ == 2 || STAGES * K_TILE >= O_TILE, "K ring too small to stage O");
+    static_assert(!QK16_ || Q_TILE == O_TILE, "O is staged over Q");
+    static constexpr int SMEM_TOTAL = SMEM_BAR + 512 + 1024;  // + barriers + alignment slack
+    static_assert(SMEM_TOTAL <= 232448, "shared memory budget exceeded");
+    static constexpr int NTHREADS = (NQ * 4 + 4) * 32;  // softmax warpgroups + one warpgroup holding the MMA / TMA warps
+    // TMEM columns
+    static constexpr int TM_S = 0;                        // S_t at t * 128 (64 columns)
+    static constexpr int TM_P = 64;                       // P(t, b) at t * 128 + 64 + b * 32
+    static constexpr int TM_O = 256;                      // O_t at 256 + t * 128 (D <= 128), single O at D = 256
+    static constexpr int TM_P_LO = 16;                    // hi/lo mode: second P tile 16 columns after the first
+    // softmax range management: p' = 2^KOFF * exp2(s - m_used), m_used may lag the true max by <= TAU (log2 units)
+    static constexpr float KOFF = V16 ? 0.f : 4.f;
+    static constexpr float TAU = V16 ? 8.f : 4.f;
+    // exponentials on the FMA pipe: polynomial degree (a single e4m3 P tolerates the quadratic's 1.7e-3)
+    static constexpr int POLY_NUM = QA_POLY_NUM;
+    static constexpr int POLY_DEG = (PMODE_ == QA_P_E4M3) ? 2 : 3;
+};
+
+struct AttnParams {
+    const float* scale_q;
+    const float* scale_k;
+    const float* scale_v;
+    float* lse;
+    int B, Hq, Hkv, Sq, Skv;
+    int causal;
+    float sm_scale_log2;  // sm_scale * log2(e)
+    int out_fp16;
+    int qk_fp16;  // QK16 configs: element type of Q and K
+    float inv_group;  // Hkv / Hq
+    long long* trace;  // developer builds (-DQA_TRACE): per-step clock64 stamps of one CTA, else unused
+    int trace_x, trace_y;
+};
+
+struct Barriers {
+    uint64_t q_full[2];
+    uint64_t k_full[4], k_empty[4], v_full[4], v_empty[4];
+    uint64_t s_full[2], s_free[2];  // [tile]: S_j written by the tensor core / pulled into registers by the softmax
+    uint64_t p_full[2][2];          // [tile][P buffer]
+    uint64_t pv_done[2][2], o_full[2];  // pv_done[tile][step parity]: PV_j complete
+    uint32_t tmem_base;
+};
+static_assert(sizeof(Barriers) <= 512, "barrier block too large");
+
+template <class C>
+__device__ __forceinline__ uint32_t qk_koff(int k) {  // byte offset of the k-th 32-byte K slice inside a Q/K tile
+    constexpr int per_box = C::QK_ROW / 32;
+    return uint32_t(k / per_box) * C::QK_BOX_BYTES + uint32_t(k % per_box) * 32u;
+}
+
+// ------------------------------------------------------------------------------------------------ exp2 helpers
+// 2^x for a pair of arguments on the FMA / ALU pipes: x = n + f with n = round(x) taken from the low mantissa bits of
+// x + 1.5 * 2^23, f in [-0.5, 0.5], 2^f by a minimax polynomial (relative error 1.7e-3 / 7.5e-5 for degree 2 / 3),
+// and n added straight into the exponent field.  Arguments are clamped at -125 (result ~ 2^-125, i.e. zero).
+template <int DEG>
+__device__ __forceinline__ float2 exp2_poly(float2 x) {
+    x.x = fmaxf(x.x, -125.f);
+    x.y = fmaxf(x.y, -125.f);
+    const float2 magic = make_float2(12582912.f, 12582912.f);
+    const float2 t = __fadd2_rn(x, magic);
+    const float2 n = __fadd2_rn(t, make_float2(-12582912.f, -12582912.f));
+    const float2 f = __ffma2_rn(n, make_float2(-1.f, -1.f), x);
+    float2 q;
+    if constexpr (DEG == 2) {
+        q = __ffma2_rn(f, make_float2(0.23842893540859222f, 0.23842893540859222f),
+                       make_float2(0.7034479975700378f, 0.7034479975700378f));
+        q = __ffma2_rn(q, f, make_float2(1.0004431009292603f, 1.0004431009292603f));
+    } else {
+        q = __ffma2_rn(f, make_float2(0.0551716685295105f, 0.0551716685295105f),
+                       make_float2(0.2426111251115799f, 0.2426111251115799f));
+        q = __ffma2_rn(q, f, make_float2(0.6932609677314758f, 0.6932609677314758f));
+        q = __ffma2_rn(q, f, make_float2(0.9999280571937561f, 0.9999280571937561f));
+    }
+    float2 r;
+    r.x = __int_as_float(__float_as_int(q.x) + (__float_as_int(t.x) << 23));
+    r.y = __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23));
+    return r;
+}
+
+__host__ __device__ constexpr bool pair_uses_poly(int i, int num) {  // spread `num` of every 8 pairs evenly
+    return (((i & 7) + 1) * num) / 8 > ((i & 7) * num) / 8;
+}
+
+template <class C, bool CAUSAL, bool TOKEN>
+__global__ void __launch_bounds__(C::NTHREADS, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, AttnParams p) {
+    constexpr int D = C::D;
+    constexpr int NQ = C::NQ;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    Barriers* bars = reinterpret_cast<Barriers*>(smem + C::SMEM_BAR);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int h = blockIdx.y, b = blockIdx.z;
+    const int hkv = int((float(h) + 0.5f) * p.inv_group);  // exact for h < 2^16; avoids an integer-division call
+    const int bh = b * p.Hq + h;
+    const int bhkv = b * p.Hkv + hkv;
+    // heavy (late) causal query blocks are scheduled first
+    const int mblk = CAUSAL ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
+    const int m0 = mblk * (BM * NQ);
+    const int nst_all = (p.Skv + BS - 1) / BS;
+    // per-tile trip counts in 64-key steps: under a causal mask tile t stops at its own diagonal
+    const int nst0 = CAUSAL ? min(nst_all, m0 / BS + 2) : nst_all;
+    const int nst1 = CAUSAL ? min(nst_all, (m0 + BM) / BS + 2) : nst_all;
+    auto n_steps = [&](int t) { return t == 0 ? nst0 : nst1; };
+    const int n_max = n_steps(NQ - 1);
+    const int n_kv = (n_max + 1) >> 1;  // K/V tiles of 128 keys
+
+    QA_STAMP(warp >> 2, 78, 0);
+    // ------------------------------------------------------------------ one-time setup
+    if (warp == 0) {
+        tmem_alloc(&bars->tmem_base, 512);
+        tmem_relinquish();
+    }
+    if (warp == 1) {  // one barrier per lane
+        if (lane < 4) {
+            const int t = lane >> 1, x = lane & 1;
+            mbar_init(x ? &bars->o_full[t] : &bars->q_full[t], 1);
+            mbar_init(&bars->pv_done[t][x], 1);
+            mbar_init(&bars->p_full[t][x], 128);
+            mbar_init(x ? &bars->s_free[t] : &bars->s_full[t], x ? 128 : 1);
+        } else if (lane < 8) {
+            const int st = lane - 4;
+            mbar_init(&bars->k_full[st], 1);
+            mbar_init(&bars->k_empty[st], NQ);  // released by every tile's MMA warp
+            mbar_init(&bars->v_full[st], 1);
+            mbar_init(&bars->v_empty[st], NQ);
+        }
+        fence_barrier_init();
+    }
+    if (warp == NQ * 4 + 1 && lane == 0) {
+        tma_prefetch_desc(&tmQ);
+        tma_prefetch_desc(&tmK);
+        tma_prefetch_desc(&tmV);
+        tma_prefetch_desc(&tmO);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (bars->tmem_base != 0) __trap();  // the CTA owns all 512 columns, so the allocation starts at column 0
+    constexpr uint32_t tmem = 0;
+
+    // register rebalancing (two-tile configs run 384 threads -> 168 registers each at launch): the softmax
+    // warpgroups keep a whole score row per thread in registers, the MMA / TMA warps need almost nothing
+    if (warp >= NQ * 4) {
+        if constexpr (NQ == 2) reg_dealloc<56>();
+        if (warp == NQ * 4 + 1) {
+            // =========================================================== TMA producer
+            if (lane == 0) {
+                for (int t = 0; t < NQ; ++t) {
+                    mbar_arrive_expect_tx(&bars->q_full[t], C::Q_TILE);
+                    for (int x = 0; x < C::QK_BOXES; ++x)
+                        tma_load_3d(smem + C::SMEM_Q + t * C::Q_TILE + x * C::QK_BOX_BYTES, &tmQ, &bars->q_full[t],
+                                    x * (C::QK_ROW / C::QB), m0 + t * BM, bh, kEvictFirst);
+                }
+                for (int n = 0; n < n_kv; ++n) {
+                    const int s = n % C::STAGES;
+                    const uint32_t ph = (n / C::STAGES) & 1;
+                    mbar_wait(&bars->k_empty[s], ph ^ 1);
+                    mbar_arrive_expect_tx(&bars->k_full[s], C::K_TILE);
+                    for (int x = 0; x < C::QK_BOXES; ++x)
+                        tma_load_3d(smem + C::SMEM_K + s * C::K_TILE + x * C::QK_BOX_BYTES, &tmK, &bars->k_full[s],
+                                    x * (C::QK_ROW / C::QB), n * BN, bhkv, kEvictLast);
+                    mbar_wait(&bars->v_empty[s], ph ^ 1);
+                    mbar_arrive_expect_tx(&bars->v_full[s], C::V_TILE);
+                    for (int x = 0; x < C::V_BOXES; ++x)
+                        tma_load_3d(smem + C::SMEM_V + s * C::V_TILE + x * C::V_BOX_BYTES, &tmV, &bars->v_full[s],
+                                    x * (C::V_ROW / C::VB), n * BN, bhkv, kEvictLast);
+                }
+            }
+        } else if (warp == NQ * 4 || (NQ == 2 && warp == NQ * 4 + 2)) {
+            // =========================================================== MMA issuers: one warp per query tile
+            // Each tile has its own chain  P_j -> PV_j -> QK_{j+2} -> S_{j+2}; a warp per tile keeps the two chains
+            // independent (a single in-order issuer would couple them) and halves the per-step instruction stream.
+            // The warp walks the loop converged; one elected lane issues.  Descriptors are built once: per MMA only
+            // the 14-bit start-address field of the low word changes.
+            const int t = (warp - NQ * 4) >> 1;
+            const int nst = n_steps(t);
+            const uint32_t qk_fmt = (C::QK16 && !p.qk_fp16) ? 1u : 0u;  // f16: 0 = fp16, 1 = bf16;  f8f6f4: 0 = e4m3
+            const uint32_t idesc_qk = make_idesc(qk_fmt, qk_fmt, 0, 0, BM, BS);
+            constexpr uint32_t idesc_pv8 = make_idesc(0, 0, 0, 1, BM, D);
+            const uint32_t idesc_pv = C::V16 ? make_idesc(p.out_fp16 ? 0 : 1, p.out_fp16 ? 0 : 1, 0, 1, BM, D) : idesc_pv8;
+            constexpr uint64_t qk_swz = (C::QK_ROW == 128) ? kSwz128 : kSwz64;
+            constexpr uint64_t v_swz = (C::V_ROW == 128) ? kSwz128 : kSwz64;
+            const uint64_t q_desc = make_smem_desc(smem_u32(smem + C::SMEM_Q + t * C::Q_TILE), 16, 8 * C::QK_ROW, qk_swz);
+            const uint64_t k_desc0 = make_smem_desc(smem_u32(smem + C::SMEM_K), 16, 8 * C::QK_ROW, qk_swz);
+            const uint64_t v_desc0 = make_smem_desc(smem_u32(smem + C::SMEM_V), C::V_BOX_BYTES, 8 * C::V_ROW, v_swz);
+            constexpr int KEYS_PER_PV = C::V16 ? 16 : 32;
+            const uint32_t s_t = C::TM_S + t * 128;
+            const uint32_t p_t0 = C::TM_P + t * 128;
+            const uint32_t o_t = C::TM_O + (NQ == 2 ? t * 128 : 0);
+
+            // S_t = Q_t . K[64 keys]^T, the keys being rows [half * 64, half * 64 + 64) of K stage `stage`
+            auto issue_qk = [&](int stage, int half) {
+                const uint64_t bd = k_desc0 + uint64_t((stage * C::K_TILE + half * (BS * C::QK_ROW)) >> 4);
+#pragma unroll
+                for (int k = 0; k < D * C::QB / 32; ++k) {  // one MMA per 32-byte K slice (32 e4m3 / 16 bf16 elements)
+                    if constexpr (C::QK16)
+                        umma_f16_ss(s_t, q_desc + (qk_koff<C>(k) >> 4), bd + (qk_koff<C>(k) >> 4), idesc_qk, k > 0);
+                    else
+                        umma_f8_ss(s_t, q_desc + (qk_koff<C>(k) >> 4), bd + (qk_koff<C>(k) >> 4), idesc_qk, k > 0);
+                }
+            };
+            // O_t (+)= P(t, half) . V[64 keys]
+            auto issue_pv = [&](int stage, int half, bool acc) {
+                const uint32_t p_t = p_t0 + half * 32;
+                const uint64_t bd = v_desc0 + uint64_t((stage * C::V_TILE + half * (BS * C::V_ROW)) >> 4);
+#pragma unroll
+                for (int k = 0; k < BS / KEYS_PER_PV; ++k) {
+                    const uint64_t bk = bd + uint64_t((k * KEYS_PER_PV * C::V_ROW) >> 4);
+                    if constexpr (!C::V16) {
+                        umma_f8_ts(o_t, p_t + k * 8, bk, idesc_pv, (acc || k > 0) ? 1u : 0u);
+                        if constexpr (C::PMODE == QA_P_E4M3_HILO) umma_f8_ts(o_t, p_t + C::TM_P_LO + k * 8, bk, idesc_pv, 1u);
+                    } else {
+                        umma_f16_ts(o_t, p_t + k * 8, bk, idesc_pv, (acc || k > 0) ? 1u : 0u);
+                    }
+                }
+            };
+
+            // prologue: S_0 and (once S_0 has been pulled) S_1 from K tile 0
+            mbar_wait(&bars->q_full[t], 0);
+            mbar_wait(&bars->k_full[0], 0);
+            tc_fence_after();
+            if (elect_one()) {
+                issue_qk(0, 0);
+                umma_commit(&bars->s_full[t]);
+                if (nst == 1) umma_commit(&bars->k_empty[0]);
+            }
+            __syncwarp();
+            if (nst > 1) {
+                mbar_wait(&bars->s_free[t], 0);
+                tc_fence_after();
+                if (elect_one()) {
+                    issue_qk(0, 1);
+                    umma_commit(&bars->s_full[t]);
+                    umma_commit(&bars->k_empty[0]);
+                }
+                __syncwarp();
+            }
+
+            // steady state, one K/V tile (two steps) per trip; the score GEMM runs two steps ahead of the PV GEMM:
+            //   [s_free(j+1) -> QK_{j+2}]  [p_full(j) -> PV_j]  [s_free(j+2) -> QK_{j+3}]  [p_full(j+1) -> PV_{j+1}]
+            int sv = 0, sk = 0;       // ring slots of the V tile feeding PV_j and of the K tile feeding QK_{j+2}
+            uint32_t pv = 0, pk = 0;  // their parities
+            uint32_t pp = 0;          // parity of p_full[t][*] (both buffers flip once per trip)
+            for (int j = 0; j < nst; j += 2) {
+                const bool has1 = j + 1 < nst, has2 = j + 2 < nst, has3 = j + 3 < nst;
+                if (++sk == C::STAGES) sk = 0, pk ^= 1;
+                if (has2) {
+                    // ---- QK_{j+2}: first half of the next K tile
+                    mbar_wait(&bars->k_full[sk], pk);
+                    mbar_wait(&bars->s_free[t], 1);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        issue_qk(sk, 0);
+                        umma_commit(&bars->s_full[t]);
+                        if (!has3) umma_commit(&bars->k_empty[sk]);
+                    }
+                    __syncwarp();
+                }
+                QA_STAMP(2 + t, j, 0);
+                // ---- PV_j: P buffer 0, first half of the V tile
+                mbar_wait(&bars->v_full[sv], pv);
+                mbar_wait(&bars->p_full[t][0], pp);
+                tc_fence_after();
+                QA_STAMP(2 + t, j, 1);
+                if (elect_one()) {
+                    issue_pv(sv, 0, j > 0);
+                    umma_commit(&bars->pv_done[t][0]);
+                    if (!has1) umma_commit(&bars->v_empty[sv]);
+                }
+                __syncwarp();
+                QA_STAMP(2 + t, j, 2);
+                if (has3) {
+                    // ---- QK_{j+3}: second half of that K tile
+                    mbar_wait(&bars->s_free[t], 0);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        issue_qk(sk, 1);
+                        umma_commit(&bars->s_full[t]);
+                        umma_commit(&bars->k_empty[sk]);
+                    }
+                    __syncwarp();
+                }
+                if (has1) {
+                    QA_STAMP(2 + t, j + 1, 0);
+                    // ---- PV_{j+1}: P buffer 1, second half of the V tile
+                    mbar_wait(&bars->p_full[t][1], pp);
+                    tc_fence_after();
+                    QA_STAMP(2 + t, j + 1, 1);
+                    if (elect_one()) {
+                        issue_pv(sv, 1, true);
+                        umma_commit(&bars->pv_done[t][1]);
+                        umma_commit(&bars->v_empty[sv]);
+                    }
+                    __syncwarp();
+                    QA_STAMP(2 + t, j + 1, 2);
+                }
+                pp ^= 1;
+                if (++sv == C::STAGES) sv = 0, pv ^= 1;
+            }
+            if (elect_one()) umma_commit(&bars->o_full[t]);
+            __syncwarp();
+        }
+    } else {
+        // =============================================================== softmax / correction / epilogue
+        if constexpr (NQ == 2) reg_alloc<224>();
+        const int t = warp >> 2;                       // query tile of this warpgroup
+        const int row = ((warp & 3) << 5) | lane;      // row inside the tile == TMEM lane
+        const uint32_t lane_base = uint32_t((warp & 3) * 32) << 16;
+        const uint32_t s_addr = tmem + lane_base + C::TM_S + t * 128;
+        const uint32_t p_base = tmem + lane_base + C::TM_P + t * 128;
+        const uint32_t o_addr = tmem + lane_base + C::TM_O + (NQ == 2 ? t * 128 : 0);
+        const int row_g = m0 + t * BM + row;
+
+        float c;  // multiplier taking raw fp8 dot products to the base-2 softmax domain
+        if constexpr (C::QK16) {
+            c = p.sm_scale_log2;
+        } else if constexpr (TOKEN) {
+            c = p.scale_q[size_t(bh) * p.Sq + min(row_g, p.Sq - 1)] * p.sm_scale_log2;
+        } else {
+            c = p.scale_q[bh] * p.scale_k[bhkv] * p.sm_scale_log2;
+        }
+        const float* sk_row = TOKEN ? p.scale_k + size_t(bhkv) * p.Skv : nullptr;
+        const float2 c2 = make_float2(c, c);
+
+        float m_used = -INFINITY;  // running max in raw score units (times per-column scale in token mode)
+        float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);  // running sum of p' (4 partial sums)
+        const int my_steps = n_steps(t);
+
+        // per-column K scales (token mode), applied to the raw scores of step j
+        auto kscale = [&](const int j, float (&s)[BS]) {
+            if constexpr (TOKEN) {
+                const int col0 = j * BS;
+                if (col0 + BS <= p.Skv && (p.Skv & 3) == 0) {  // rows of scale_k stay 16-byte aligned
+#pragma unroll
+                    for (int i = 0; i < BS; i += 4) {
+                        float4 k4 = __ldg(reinterpret_cast<const float4*>(sk_row + col0 + i));
+                        s[i] *= k4.x, s[i + 1] *= k4.y, s[i + 2] *= k4.z, s[i + 3] *= k4.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < BS; ++i) s[i] *= __ldg(sk_row + min(col0 + i, p.Skv - 1));
+                }
+            }
+        };
+        // causal / ragged mask of step j.  Only the trailing steps of a tile can need it (the ragged tail is the last
+        // step, the causal diagonal the last two), so it is instantiated in the tail loop only: the main loop below
+        // carries no mask code at all and stays a compact straight line for the instruction cache.
+        auto mask = [&](const int j, float (&s)[BS]) {
+            const int col0 = j * BS;
+            const bool tail = col0 + BS > p.Skv;
+            const bool diag = CAUSAL && (col0 + BS - 1 > m0 + t * BM);
+            if (tail || diag) {
+                const int lim = CAUSAL ? min(p.Skv - 1, row_g) : (p.Skv - 1);  // last visible column
+#pragma unroll
+                for (int i = 0; i < BS; ++i)
+                    if (col0 + i > lim) s[i] = -INFINITY;
+            }
+        };
+        // first step whose scores need the mask (every later one does too)
+        const int j_mask = CAUSAL ? min(p.Skv / BS, (m0 + t * BM) / BS) : p.Skv / BS;
+        // row maximum of sixteen columns folded into two running maxima (two chains per call site -> four in flight)
+        auto max16 = [&](const float (&s)[BS], int q, float& ma, float& mb) {
+#pragma unroll
+            for (int i = 16 * q; i < 16 * q + 16; i += 4) {
+                ma = fmaxf(ma, fmaxf(s[i], s[i + 1]));
+                mb = fmaxf(mb, fmaxf(s[i + 2], s[i + 3]));
+            }
+        };
+        // rare: the running maximum of some row of this warp grew by more than 2^TAU -> rescale O (rolled: cold code)
+        auto rescale_o = [&](const float alpha) {
+#pragma unroll 1
+            for (int cc = 0; cc < D; cc += 32) {
+                float o[32];
+                tmem_ld_x32(o_addr + cc, o);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o[i] *= alpha;
+                tmem_st_x32(o_addr + cc, o);
+            }
+            tmem_st_wait();
+        };
+
+        // One 64-key step.  On entry `s` holds S_j (scaled / masked as needed) and `mx` its row maximum.  The step turns
+        // S_j into P_j.  Unless it is the last step it also pulls S_{j+1} into `s_next` after LOADQ quads of
+        // exponentials, frees the score buffer for QK_{j+2}, and folds the row maximum of S_{j+1} into the remaining
+        // exponentials; it returns that maximum.  The code between the few waits is straight-line on purpose: every
+        // branch is a scheduling barrier at which the exp pipeline of this warp drains.
+        //   MASKED (compile time): S_{j+1} may need the causal / ragged mask;  `last`: there is no S_{j+1}.
+        constexpr int LOADQ = QA_LOADQ;  // quad index (of 16) before which the load of S_{j+1} is issued
+        static_assert(LOADQ >= 2 && LOADQ <= 12 && LOADQ % 2 == 0, "LOADQ");
+        auto step = [&](const int j, float (&s)[BS], float (&s_next)[BS], const float mx, auto mask_tag,
+                        const bool last) -> float {
+            constexpr bool MASKED = decltype(mask_tag)::value;
+            QA_STAMP(t, j, 0);
+            const float m_new = fmaxf(m_used, mx);
+            bool p_prev_pending = j > 0;  // P_{j-1} is stored but not yet published (see below)
+            // lazy rescale: keep the stale max while the true max has grown by < 2^TAU
+            const bool grow = (m_new - m_used) * c > C::TAU;
+            if (__builtin_expect(__any_sync(0xffffffffu, grow), 0)) {
+                const float alpha = ex2_approx((m_used - m_new) * c);  // 0 on the first step
+                m_used = m_new;
+                la.x *= alpha, la.y *= alpha, lb.x *= alpha, lb.y *= alpha;
+                if (j > 0) {
+                    // O_t must be quiescent: PV_{j-1} is the only MMA that can still be writing it - and it cannot
+                    // even start before P_{j-1} is published
+                    tmem_st_wait();
+                    tc_fence_before();
+                    mbar_arrive(&bars->p_full[t][(j - 1) & 1]);
+                    p_prev_pending = false;
+                    // (one barrier per step parity: PV_{j-3}, the previous phase of this barrier, is known to be
+                    // complete because S_j has been seen, so the parity test cannot alias)
+                    mbar_wait(&bars->pv_done[t][(j - 1) & 1], ((j - 1) >> 1) & 1);
+                    tc_fence_after();
+                    rescale_o(alpha);
+                }
+            }
+            const float neg = C::KOFF - m_used * c;
+            const float2 neg2 = make_float2(neg, neg);
+            QA_STAMP(t, j, 1);
+
+            // p' for one pair of columns; a compile-time subset of the pairs avoids MUFU
+            auto exp_pair = [&](int i) -> float2 {
+                const float2 x = __ffma2_rn(make_float2(s[2 * i], s[2 * i + 1]), c2, neg2);
+                if (pair_uses_poly(i, C::POLY_NUM)) return exp2_poly<C::POLY_DEG>(x);
+                return make_float2(ex2_approx(x.x), ex2_approx(x.y));
+            };
+            uint32_t pw[C::V16 ? BS / 2 : BS / 4], pw_lo[C::PMODE == QA_P_E4M3_HILO ? BS / 4 : 1];
+            // four columns -> P words
+            auto exp_quad = [&](int i) {
+                const float2 p01 = exp_pair(2 * i), p23 = exp_pair(2 * i + 1);
+                la = __fadd2_rn(la, p01);
+                lb = __fadd2_rn(lb, p23);
+                if constexpr (C::PMODE == QA_P_E4M3) {
+                    pw[i] = pack_e4m3x4(p01.x, p01.y, p23.x, p23.y);
+                } else if constexpr (C::PMODE == QA_P_E4M3_HILO) {
+                    const uint32_t h01 = cvt_e4m3x2(p01.x, p01.y), h23 = cvt_e4m3x2(p23.x, p23.y);
+                    const float2 f01 = e4m3x2_to_float2(h01), f23 = e4m3x2_to_float2(h23);
+                    pw[i] = h01 | (h23 << 16);
+                    pw_lo[i] = pack_e4m3x4(p01.x - f01.x, p01.y - f01.y, p23.x - f23.x, p23.y - f23.y);
+                } else {
+                    pw[2 * i] = p.out_fp16 ? pack_f16x2(p01.x, p01.y) : pack_bf16x2(p01.x, p01.y);
+                    pw[2 * i + 1] = p.out_fp16 ? pack_f16x2(p23.x, p23.y) : pack_bf16x2(p23.x, p23.y);
+                }
+            };
+
+#pragma unroll
+            for (int i = 0; i < 2; ++i) exp_quad(i);
+            if (p_prev_pending) {  // P_{j-1} was stored at the end of the previous step: publish it now
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(&bars->p_full[t][(j - 1) & 1]);
+            }
+#pragma unroll
+            for (int i = 2; i < LOADQ; ++i) exp_quad(i);
+            float ma = -INFINITY, mb = -INFINITY;
+            if (!last) {
+                // S_{j+1} was issued by the tensor core when this thread released S_j, about one step ago
+                mbar_wait(&bars->s_full[t], (j + 1) & 1);
+                tc_fence_after();
+                tmem_ld_f64(s_addr, s_next);
+                QA_STAMP(t, j, 2);
+#pragma unroll
+                for (int i = LOADQ; i < LOADQ + 2; ++i) exp_quad(i);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(&bars->s_free[t]);  // the score buffer may be overwritten by QK_{j+2}
+                kscale(j + 1, s_next);
+                if constexpr (MASKED) mask(j + 1, s_next);
+                QA_STAMP(t, j, 3);
+                // the row maximum of S_{j+1} is spread over the remaining quads, four 16-column pieces in all
+                constexpr int REST = 14 - LOADQ;              // quads left
+                constexpr int PER = (4 + REST - 1) / REST;    // pieces per quad (2 at LOADQ = 12, 1 from LOADQ <= 10)
+#pragma unroll
+                for (int i = LOADQ + 2; i < 16; ++i) {
+                    exp_quad(i);
+#pragma unroll
+                    for (int q = 0; q < PER; ++q) {
+                        const int piece = (i - LOADQ - 2) * PER + q;
+                        if (piece < 4) max16(s_next, piece, ma, mb);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int i = LOADQ; i < 16; ++i) exp_quad(i);
+                // P buffer reuse: PV_{j-2} must have drained it.  Seeing S_{j+1} (issued after PV_{j-2}, in-order
+                // tensor pipe) proves that in every other step; the last one waits for PV_{j-1} explicitly.
+                if (j >= 2) mbar_wait(&bars->pv_done[t][(j - 1) & 1], ((j - 1) >> 1) & 1);
+            }
+            const uint32_t p_addr = p_base + (j & 1) * 32;
+            if constexpr (C::PMODE == QA_P_E4M3) {
+                tmem_st_u16(p_addr, pw);
+            } else if constexpr (C::PMODE == QA_P_E4M3_HILO) {
+                tmem_st_u16(p_addr, pw);
+                tmem_st_u16(p_addr + C::TM_P_LO, pw_lo);
+            } else {
+                tmem_st_u32(p_addr, pw);
+            }
+            if (last) {  // nothing left to hide the store behind
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(&bars->p_full[t][j & 1]);
+            }
+            QA_STAMP(t, j, 4);
+            return fmaxf(ma, mb);
+        };
+
+#ifdef QA_STAGGER
+        if (t == 1) {  // start the second tile's softmax out of phase with the first
+            const long long t_go = clock64() + QA_STAGGER;
+            while (clock64() < t_go) {
+            }
+        }
+#endif
+        float s_a[BS], s_b[BS];
+        float mx;
+        QA_STAMP(t, 78, 1);
+        {   // S_0
+            mbar_wait(&bars->s_full[t], 0);
+            QA_STAMP(t, 78, 2);
+            tc_fence_after();
+            tmem_ld_f64(s_addr, s_a);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(&bars->s_free[t]);
+            kscale(0, s_a);
+            mask(0, s_a);
+            float ma = -INFINITY, mb = -INFINITY;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) max16(s_a, q, ma, mb);
+            mx = fmaxf(ma, mb);
+        }
+        {
+            using std::false_type;
+            using std::true_type;
+            // main loop: steps whose successor exists and needs no mask, two per trip (the score registers ping-pong)
+            const int n_fast = min(my_steps - 1, j_mask - 1);
+            int j = 0;
+            for (; j + 2 <= n_fast; j += 2) {
+                mx = step(j, s_a, s_b, mx, false_type{}, false);
+                mx = step(j + 1, s_b, s_a, mx, false_type{}, false);
+            }
+            // tail: the few steps around the causal diagonal / ragged end, and the last one (rolled, one instance)
+#pragma unroll 1
+            for (; j < my_steps; ++j) {
+                mx = step(j, s_a, s_b, mx, true_type{}, j + 1 == my_steps);
+#pragma unroll
+                for (int i = 0; i < BS; ++i) s_a[i] = s_b[i];
+            }
+        }
+        const float l = (la.x + la.y) + (lb.x + lb.y);
+        QA_STAMP(t, 78, 3);
+
+        // ---------------------------------------------------------------- epilogue: O / l -> 16 bit -> smem -> TMA
+        mbar_wait(&bars->o_full[t], 0);
+        tc_fence_after();
+        QA_STAMP(t, 78, 4);
+        const float sv = C::V16 ? 1.f : p.scale_v[bhkv];
+        const float inv = __fdividef(sv, l);
+        uint8_t* o_smem = smem + C::SMEM_O + t * C::O_TILE;
+#pragma unroll
+        for (int cc = 0; cc < D; cc += 32) {
+            float o[32];
+            tmem_ld_x32(o_addr + cc, o);
+            tmem_ld_wait();
+            uint32_t w[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float a = o[2 * i] * inv, bb = o[2 * i + 1] * inv;
+                w[i] = p.out_fp16 ? pack_f16x2(a, bb) : pack_bf16x2(a, bb);
+            }
+            // 64 output columns (128 bytes) per box row, 128B-swizzled so the TMA store un-swizzles it
+            uint8_t* box = o_smem + (cc >> 6) * (BM * 128) + row * 128;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int chunk = ((cc & 63) >> 3) + q;
+                *reinterpret_cast<uint4*>(box + ((chunk ^ (row & 7)) << 4)) =
+                    make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+            }
+        }
+        if (p.lse != nullptr && row_g < p.Sq)
+            p.lse[size_t(bh) * p.Sq + row_g] = (m_used * c + (__log2f(l) - C::KOFF)) * 0.6931471805599453f;
+        fence_proxy_async_smem();
+        named_bar_sync(1 + t, 128);
+        if ((warp & 3) == 0 && lane == 0 && m0 + t * BM < p.Sq) {
+            for (int x = 0; x < C::O_BOXES; ++x) tma_store_3d(&tmO, o_smem + x * (BM * 128), x * 64, m0 + t * BM, bh);
+            tma_store_commit();
+            tma_store_wait_read<0>();  // the CTA only has to keep its shared memory alive until it has been read
+        }
+        QA_STAMP(t, 78, 5);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+    QA_STAMP(warp >> 2, 78, 6);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+template <class C, bool CAUSAL, bool TOKEN>
+static int launch_cfg(const AttnArgs& a, cudaStream_t stream, int* launches) {
+    CUtensorMap tmQ, tmK, tmV, tmO;
+    const CUtensorMapSwizzle qk_swz = C::QK_ROW == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    const CUtensorMapSwizzle v_swz = C::V_ROW == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    const uint64_t D = C::D;
+    bool ok = true;
+    const CUtensorMapDataType qkdt = !C::QK16 ? CU_TENSOR_MAP_DATA_TYPE_UINT8
+                                     : (a.qk_dtype == QA_DT_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                                                 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+    ok &= make_tmap_3d(&tmQ, qkdt, C::QB, a.q8, D, a.Sq, uint64_t(a.B) * a.Hq, D * C::QB, D * C::QB * a.Sq,
+                       C::QK_ROW / C::QB, BM, qk_swz);
+    ok &= make_tmap_3d(&tmK, qkdt, C::QB, a.k8, D, a.Skv, uint64_t(a.B) * a.Hkv, D * C::QB, D * C::QB * a.Skv,
+                       C::QK_ROW / C::QB, BN, qk_swz);
+    if (C::V16) {
+        const CUtensorMapDataType dt =
+            a.v_dtype == QA_DT_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+        ok &= make_tmap_3d(&tmV, dt, 2, a.v, D, a.Skv, uint64_t(a.B) * a.Hkv, D * 2, D * 2 * a.Skv, C::V_ROW / 2, BN,
+                           v_swz);
+    } else {
+        ok &= make_tmap_3d(&tmV, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, a.v, D, a.Skv, uint64_t(a.B) * a.Hkv, D, D * a.Skv,
+                           C::V_ROW, BN, v_swz);
+    }
+    const CUtensorMapDataType odt =
+        a.out_dtype == QA_DT_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    ok &= make_tmap_3d(&tmO, odt, 2, a.out, D, a.Sq, uint64_t(a.B) * a.Hq, D * 2, D * 2 * a.Sq, 64, BM,
+                       CU_TENSOR_MAP_SWIZZLE_128B);
+    if (!ok) return set_error(QA_ERR_DEVICE, "cuTensorMapEncodeTiled failed or is unavailable (no CUDA driver?)");
+
+    AttnParams p;
+    p.scale_q = a.scale_q;
+    p.scale_k = a.scale_k;
+    p.scale_v = a.scale_v;
+    p.lse = a.lse;
+    p.B = a.B, p.Hq = a.Hq, p.Hkv = a.Hkv, p.Sq = a.Sq, p.Skv = a.Skv;
+    p.causal = a.causal;
+    p.sm_scale_log2 = a.sm_scale * kLog2e;
+    p.out_fp16 = (a.out_dtype == QA_DT_FP16);
+    p.qk_fp16 = (a.qk_dtype == QA_DT_FP16);
+    p.inv_group = float(a.Hkv) / float(a.Hq);
+#ifdef QA_TRACE
+    p.trace = g_trace_ptr;
+    p.trace_x = g_trace_x, p.trace_y = g_trace_y;
+#else
+    p.trace = nullptr;
+    p.trace_x = p.trace_y = 0;
+#endif
+
+    auto kern = attn_fwd_kernel<C, CAUSAL, TOKEN>;
+    static bool attr_done = false;  // per instantiation; racing threads set the same value
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_TOTAL);
+        if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(max dynamic smem)", e);
+        attr_done = true;
+    }
+    dim3 grid((a.Sq + BM * C::NQ - 1) / (BM * C::NQ), a.Hq, a.B);
+    kern<<<grid, C::NTHREADS, C::SMEM_TOTAL, stream>>>(tmQ, tmK, tmV, tmO, p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error("attn_fwd_kernel launch", e);
+    *launches += 1;
+    return QA_OK;
+}
+
+}  // namespace qa

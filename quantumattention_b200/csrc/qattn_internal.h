@@ -37,6 +37,7 @@ struct AttnArgs {
     int p_mode;
     int v_dtype;
     int out_dtype;
+    int qk_dtype;  // QA_DT_E4M3 (FP8 path) or QA_DT_BF16 / QA_DT_FP16 (16-bit path)
 };
 
 struct MergeArgs {
@@ -55,7 +56,8 @@ int set_error(int code, const char* fmt, ...);
 int set_cuda_error(const char* what, cudaError_t e);
 
 int quantize_dispatch(QuantArgs& a, int x_dtype, int scale_mode, int n_tensors, cudaStream_t stream, int* launches);
-int attn_fwd_dispatch(const AttnArgs& a, cudaStream_t stream, int* launches);
+int attn_fwd_dispatch(const AttnArgs& a, cudaStream_t stream, int* launches);    // e4m3 Q / K
+int attn16_fwd_dispatch(const AttnArgs& a, cudaStream_t stream, int* launches);  // bf16 / fp16 Q / K
 int merge_dispatch(const MergeArgs& a, cudaStream_t stream, int* launches);
 
 }  // namespace qa

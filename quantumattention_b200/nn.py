@@ -163,8 +163,6 @@ def can_use_attention(query, key, value, attn_mask=None, dropout_p=0.0, is_causa
     if ok:
         ok, reason = _validate_input(query, key, value, attn_mask, dropout_p, is_causal, scale, scaling_method,
                                      scale_q, scale_k)
-    if ok and scaling_method is None:
-        ok, reason = False, "NYI: the 16-bit attention kernel is not built for sm_100a yet (use fp8_attn_func)"
     return (True, "") if ok else (False, f"[sm100_tcgen05: {reason}]")
 
 
@@ -246,12 +244,18 @@ def fp8_attention(query, key, value, attn_mask=None, dropout_p=0.0, is_causal=Fa
 
 
 def attention(query, key, value, attn_mask=None, dropout_p=0.0, is_causal=False, *, scale=None) -> torch.Tensor:
-    """16-bit attention entry point (reference: src/quantum_attn/nn.py:325-391).  Next on the list."""
+    """16-bit attention entry point (reference: src/quantum_attn/nn.py:325-391): bf16 / fp16 q, k, v straight into the
+    fused kernel (kind::f16 MMAs), no quantisation."""
     supported, reason = can_use_attention(
         query, key, value, attn_mask=attn_mask, dropout_p=dropout_p, is_causal=is_causal, scale=scale
     )
     if not supported:
         raise ValueError(f"Unsupported input: {reason}")
+    from torch._subclasses.fake_tensor import is_fake
+
+    traced = torch.compiler.is_dynamo_compiling() or any(is_fake(x) for x in (query, key, value))
+    if not traced and not config.attention.force_eager_fallback:
+        return ops.attention_native(query, key, value, is_causal=is_causal, scale=scale)  # no dispatcher hop
     return torch.ops.quantum_attn.attention_forward(
         query, key, value, attn_mask=attn_mask, dropout_p=dropout_p, is_causal=is_causal, scale=scale
     )

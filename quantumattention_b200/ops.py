@@ -49,6 +49,24 @@ def fp8_attention_definition(query, key, value, scale_q=None, scale_k=None, attn
     ).contiguous()
 
 
+def attention_definition(query, key, value, attn_mask=None, dropout_p=0.0, is_causal=False, *, scale=None):
+    """What the 16-bit op computes, stated with aten ops (reference: src/quantum_attn/ops.py:27-29)."""
+    if key.size(1) != query.size(1):  # GQA (extension; the reference's Python gate forbids it)
+        rep = query.size(1) // key.size(1)
+        key, value = key.repeat_interleave(rep, 1), value.repeat_interleave(rep, 1)
+    return aten.scaled_dot_product_attention(
+        query, key, value, attn_mask=attn_mask, dropout_p=dropout_p, is_causal=is_causal, scale=scale
+    ).contiguous()
+
+
+def attention_native(query, key, value, is_causal=False, scale=None, return_lse=False):
+    """16-bit q, k, v -> attention output through the sm_100a kernel (no fallback)."""
+    if query.dtype not in (torch.float16, torch.bfloat16) or key.dtype != query.dtype or value.dtype != query.dtype:
+        raise ValueError("attention_forward expects query, key and value of one dtype, torch.float16 or torch.bfloat16")
+    sm_scale = (1.0 / math.sqrt(query.size(-1))) if scale is None else float(scale)
+    return _native.attn_fwd(query, key, value, is_causal=is_causal, sm_scale=sm_scale, return_lse=return_lse)
+
+
 def _scale_mode_of(scale_q: torch.Tensor, query: torch.Tensor) -> int:
     if scale_q.dim() == query.dim() - 2:
         return _native.QA_SCALE_HEAD
@@ -116,8 +134,12 @@ def attention_forward(
     *,
     scale: Optional[float] = None,
 ) -> torch.Tensor:
-    # 16-bit QK^T path (reference: src/quantum_attn/ops.py:32-45).  Not part of the FP8 hot path; SURVEY §8(f) rank 1.
-    raise ValueError("NYI: the 16-bit attention_forward kernel is not built yet on sm_100a (FP8 path only)")
+    # 16-bit QK^T path (reference: src/quantum_attn/ops.py:32-45): the same fused kernel with kind::f16 MMAs
+    if attn_mask is not None or dropout_p != 0.0:
+        raise ValueError("NYI: attn_mask must be None and dropout_p must be 0.0")
+    if config.attention.force_eager_fallback:
+        return attention_definition(query, key, value, attn_mask, dropout_p, is_causal, scale=scale)
+    return attention_native(query, key, value, is_causal=is_causal, scale=scale)
 
 
 @torch.library.register_fake("quantum_attn::attention_forward")

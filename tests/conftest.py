@@ -23,3 +23,10 @@ def bf16_from_bits(bits):
     import torch
 
     return torch.from_numpy(bits.copy()).view(torch.bfloat16)
+
+
+def f16_from_bits(bits, fp16):
+    """int16 bit patterns -> torch.float16 (fp16 truthy) or torch.bfloat16 tensor."""
+    import torch
+
+    return torch.from_numpy(bits.copy()).view(torch.float16 if fp16 else torch.bfloat16)

@@ -46,9 +46,15 @@ def test_argument_validation_without_gpu():
     assert rc == -1 and b"multiple of Hkv" in lib.qa_last_error()
     rc = lib.qa_fp8_attn_fwd(16, 16, 16, 0, 16, 16, None, 0, 16, 0, None, 1, 2, 2, 8, 8, 64, 0, 0.125, 0, None)
     assert rc == -1  # fp8 P mode with a 16-bit V
+    rc = lib.qa_attn_fwd(16, 16, 16, 2, 16, None, 1, 2, 2, 8, 8, 64, 0, 0.125, None)
+    assert rc == -1 and b"fp16 or bf16" in lib.qa_last_error()  # e4m3 inputs belong to qa_fp8_attn_fwd
+    rc = lib.qa_attn_fwd(16, 16, 16, 0, 16, None, 1, 2, 2, 8, 8, 96, 0, 0.125, None)
+    assert rc == -1 and b"Unsupported head dimension: 96" in lib.qa_last_error()
     import torch
 
     if not torch.cuda.is_available():
         # valid arguments but no device: must fail loudly, never fall back
         rc = lib.qa_fp8_attn_fwd(16, 16, 16, 2, 16, 16, 16, 0, 16, 0, None, 1, 2, 2, 8, 8, 64, 0, 0.125, 0, None)
+        assert rc in (-2, -3)
+        rc = lib.qa_attn_fwd(16, 16, 16, 0, 16, None, 1, 2, 2, 8, 8, 64, 0, 0.125, None)
         assert rc in (-2, -3)
