@@ -25,6 +25,7 @@
 // Deliberately absent: any non-sm_100 path, any fallback.
 #pragma once
 #include <cmath>
+#include <cstdio>
 #include <type_traits>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -55,7 +56,16 @@ constexpr float kLog2e = 1.4426950408889634f;
 #define QA_POLY_NUM 2  // of every 8 pairs of exponentials, how many run on the FMA pipe instead of MUFU
 #endif
 #ifndef QA_LOADQ
-#define QA_LOADQ 12    // S_{j+1} is pulled into registers after this many (of 16) quads of step j's exponentials
+#define QA_LOADQ 10    // S_{j+1} is pulled into registers after this many (of 16) quads of step j's exponentials
+#endif
+#ifndef QA_SWP
+#define QA_SWP 0       // software-pipeline depth of the exponentials, in quads (0: issue and consume in the same slot)
+#endif
+#ifndef QA_FENCEQ
+#define QA_FENCEQ 2    // a scheduling fence after every QA_FENCEQ-th quad
+#endif
+#ifndef QA_DECIDEQ
+#define QA_DECIDEQ 1   // quads of exponentials left when the rescale decision for the next step is taken
 #endif
 
 // QK16_: Q and K stay 16-bit (bf16 / fp16) and QK^T runs as kind::f16 - the reference's `attn_func` path
@@ -124,6 +134,7 @@ struct AttnParams {
     float inv_group;  // Hkv / Hq
     long long* trace;  // developer builds (-DQA_TRACE): per-step clock64 stamps of one CTA, else unused
     int trace_x, trace_y;
+    int sched_fence;  // always 0: an opaque value for never-taken branches that keep ptxas from merging code regions
 };
 
 struct Barriers {
@@ -486,15 +497,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         //   MASKED (compile time): S_{j+1} may need the causal / ragged mask;  `last`: there is no S_{j+1}.
         constexpr int LOADQ = QA_LOADQ;  // quad index (of 16) before which the load of S_{j+1} is issued
         static_assert(LOADQ >= 2 && LOADQ <= 12 && LOADQ % 2 == 0, "LOADQ");
-        auto step = [&](const int j, float (&s)[BS], float (&s_next)[BS], const float mx, auto mask_tag,
-                        const bool last) -> float {
+        //   `need` (warp-uniform): some row of the warp has outgrown its stale maximum, as decided near the END of the
+        //   previous step (see below) - so the common case enters the exponentials with nothing to wait for.
+        auto step = [&](const int j, float (&s)[BS], float (&s_next)[BS], const float mx, bool& need, auto mask_tag,
+                        auto inst_tag, const bool last) -> float {
             constexpr bool MASKED = decltype(mask_tag)::value;
+            constexpr int INST = decltype(inst_tag)::value;  // which copy of the step this is (distinct fence constants)
             QA_STAMP(t, j, 0);
-            const float m_new = fmaxf(m_used, mx);
             bool p_prev_pending = j > 0;  // P_{j-1} is stored but not yet published (see below)
             // lazy rescale: keep the stale max while the true max has grown by < 2^TAU
-            const bool grow = (m_new - m_used) * c > C::TAU;
-            if (__builtin_expect(__any_sync(0xffffffffu, grow), 0)) {
+            if (__builtin_expect(need, 0)) {
+                const float m_new = fmaxf(m_used, mx);
                 const float alpha = ex2_approx((m_used - m_new) * c);  // 0 on the first step
                 m_used = m_new;
                 la.x *= alpha, la.y *= alpha, lb.x *= alpha, lb.y *= alpha;
@@ -523,11 +536,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 return make_float2(ex2_approx(x.x), ex2_approx(x.y));
             };
             uint32_t pw[C::V16 ? BS / 2 : BS / 4], pw_lo[C::PMODE == QA_P_E4M3_HILO ? BS / 4 : 1];
-            // four columns -> P words
-            auto exp_quad = [&](int i) {
-                const float2 p01 = exp_pair(2 * i), p23 = exp_pair(2 * i + 1);
+            // Four columns per "quad".  The quad is software-pipelined by hand: quad i's exponentials are ISSUED (scale
+            // FFMA2 + MUFU.EX2, or the polynomial) in slot i and their results are CONSUMED (row sum, conversion to the P
+            // words) in slot i + SWP.  ptxas would otherwise sink all MUFUs of a basic block to its end, right in front
+            // of their consumers, and an in-order warp then alternates between an FMA-only stretch and a stall on the
+            // MUFU latency; a never-taken branch on an opaque kernel parameter after every slot keeps the slots apart.
+            constexpr int SWP = QA_SWP;
+            float2 pa[16], pb[16];
+            auto produce = [&](int i) {
+                pa[i] = exp_pair(2 * i);
+                pb[i] = exp_pair(2 * i + 1);
+            };
+            auto consume = [&](int i) {
+                const float2 p01 = pa[i], p23 = pb[i];
+#ifndef QA_EXP_NOSUM
                 la = __fadd2_rn(la, p01);
                 lb = __fadd2_rn(lb, p23);
+#else
+                if (i == 0) { la = __fadd2_rn(la, p01); lb = __fadd2_rn(lb, p23); }
+#endif
                 if constexpr (C::PMODE == QA_P_E4M3) {
                     pw[i] = pack_e4m3x4(p01.x, p01.y, p23.x, p23.y);
                 } else if constexpr (C::PMODE == QA_P_E4M3_HILO) {
@@ -539,6 +566,36 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     pw[2 * i] = p.out_fp16 ? pack_f16x2(p01.x, p01.y) : pack_bf16x2(p01.x, p01.y);
                     pw[2 * i + 1] = p.out_fp16 ? pack_f16x2(p23.x, p23.y) : pack_bf16x2(p23.x, p23.y);
                 }
+            };
+            // slot i; `extra` is other work that belongs into the same slot (a piece of the next row maximum)
+            auto exp_slot = [&](int i, auto extra) {
+#ifdef QA_EXP_LONE
+                if constexpr (decltype(mask_tag)::value) { pw[C::V16 ? 2 * i : i] = 0; extra(); return; }
+#endif
+                if (SWP > 0 && (i % QA_FENCEQ) == QA_FENCEQ - 1) {
+                    // the slot is the body of a do-while whose back edge is never taken (p.sched_fence is always 0,
+                    // which ptxas cannot know): a basic block of its own, at the price of a compare and a
+                    // fall-through branch
+                    int never;
+                    do {
+                        produce(i);
+                        if (i >= SWP) consume(i - SWP);
+                        extra();
+                        asm volatile("mov.b32 %0, %1;" : "=r"(never) : "r"(p.sched_fence));
+                    } while (__builtin_expect(never == i + 1 + 16 * INST, 0));
+                } else {
+                    produce(i);
+                    if (i >= SWP) consume(i - SWP);
+                    extra();
+                }
+            };
+            auto exp_quad = [&](int i) { exp_slot(i, [] {}); };
+            auto exp_drain = [&]() {  // results of the last SWP quads
+#ifdef QA_EXP_LONE
+                if constexpr (decltype(mask_tag)::value) return;
+#endif
+#pragma unroll
+                for (int i = 16 - SWP; i < 16; ++i) consume(i);
             };
 
 #pragma unroll
@@ -565,21 +622,32 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 kscale(j + 1, s_next);
                 if constexpr (MASKED) mask(j + 1, s_next);
                 QA_STAMP(t, j, 3);
-                // the row maximum of S_{j+1} is spread over the remaining quads, four 16-column pieces in all
-                constexpr int REST = 14 - LOADQ;              // quads left
-                constexpr int PER = (4 + REST - 1) / REST;    // pieces per quad (2 at LOADQ = 12, 1 from LOADQ <= 10)
+                // the row maximum of S_{j+1} is spread over the remaining quads but the last QA_DECIDEQ, four 16-column
+                // pieces in all; the rescale decision for step j + 1 (a warp vote) is taken before those last quads, whose
+                // exponentials hide its latency
+                constexpr int DECQ = QA_DECIDEQ;
+                constexpr int REST = 14 - LOADQ - DECQ;       // quads carrying a piece of the maximum
+                static_assert(REST >= 1, "LOADQ / QA_DECIDEQ leave no room for the row maximum");
+                constexpr int PER = (4 + REST - 1) / REST;    // pieces per quad
 #pragma unroll
-                for (int i = LOADQ + 2; i < 16; ++i) {
-                    exp_quad(i);
+                for (int i = LOADQ + 2; i < 16 - DECQ; ++i) {
+                    exp_slot(i, [&] {
 #pragma unroll
-                    for (int q = 0; q < PER; ++q) {
-                        const int piece = (i - LOADQ - 2) * PER + q;
-                        if (piece < 4) max16(s_next, piece, ma, mb);
-                    }
+                        for (int q = 0; q < PER; ++q) {
+                            const int piece = (i - LOADQ - 2) * PER + q;
+                            if (piece < 4) max16(s_next, piece, ma, mb);
+                        }
+                    });
                 }
+                need = __any_sync(0xffffffffu, (fmaxf(ma, mb) - m_used) * c > C::TAU);
+#pragma unroll
+                for (int i = 16 - DECQ; i < 16; ++i) exp_quad(i);
+                exp_drain();
             } else {
+                need = false;
 #pragma unroll
                 for (int i = LOADQ; i < 16; ++i) exp_quad(i);
+                exp_drain();
                 // P buffer reuse: PV_{j-2} must have drained it.  Seeing S_{j+1} (issued after PV_{j-2}, in-order
                 // tensor pipe) proves that in every other step; the last one waits for PV_{j-1} explicitly.
                 if (j >= 2) mbar_wait(&bars->pv_done[t][(j - 1) & 1], ((j - 1) >> 1) & 1);
@@ -631,16 +699,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             using std::false_type;
             using std::true_type;
             // main loop: steps whose successor exists and needs no mask, two per trip (the score registers ping-pong)
+#ifdef QA_EXP_LONE  // experiment: tile 1 skips its exponentials (it runs the masked instance only, which is stubbed)
+            const int n_fast = t == 1 ? 0 : min(my_steps - 1, j_mask - 1);
+#else
             const int n_fast = min(my_steps - 1, j_mask - 1);
+#endif
             int j = 0;
+            bool need = true;  // first step: m_used = -inf
             for (; j + 2 <= n_fast; j += 2) {
-                mx = step(j, s_a, s_b, mx, false_type{}, false);
-                mx = step(j + 1, s_b, s_a, mx, false_type{}, false);
+                mx = step(j, s_a, s_b, mx, need, false_type{}, std::integral_constant<int, 0>{}, false);
+                mx = step(j + 1, s_b, s_a, mx, need, false_type{}, std::integral_constant<int, 1>{}, false);
             }
             // tail: the few steps around the causal diagonal / ragged end, and the last one (rolled, one instance)
 #pragma unroll 1
             for (; j < my_steps; ++j) {
-                mx = step(j, s_a, s_b, mx, true_type{}, j + 1 == my_steps);
+                mx = step(j, s_a, s_b, mx, need, true_type{}, std::integral_constant<int, 2>{}, j + 1 == my_steps);
 #pragma unroll
                 for (int i = 0; i < BS; ++i) s_a[i] = s_b[i];
             }
@@ -741,6 +814,7 @@ static int launch_cfg(const AttnArgs& a, cudaStream_t stream, int* launches) {
     p.trace = nullptr;
     p.trace_x = p.trace_y = 0;
 #endif
+    p.sched_fence = 0;
 
     auto kern = attn_fwd_kernel<C, CAUSAL, TOKEN>;
     static bool attr_done = false;  // per instantiation; racing threads set the same value

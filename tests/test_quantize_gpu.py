@@ -1,5 +1,6 @@
 """Parity of the sm_100a quantiser with the oracle: BIT-EXACT bytes and scales (integer / byte work)."""
 import os
+import zlib
 
 import numpy as np
 import pytest
@@ -41,9 +42,23 @@ def test_golden_vectors_from_reference(golden_dir, mode, file):
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("shape", [(2, 8, 512, 64), (1, 3, 999, 128), (1, 2, 1000, 256), (1, 1, 1, 64), (2, 2, 17, 128)])
 def test_random_inputs(mode, dtype, shape):
-    g = torch.Generator().manual_seed(hash((mode, str(dtype), shape)) % (2**31))
+    # (zlib.crc32, not hash(): str hashes are salted per process and the test must draw the same tensors every run)
+    g = torch.Generator().manual_seed(zlib.crc32(repr((mode, str(dtype), shape)).encode()))
     x = (torch.randn(shape, generator=g) * torch.exp(torch.randn(shape[:2] + (1, shape[3]), generator=g))).to(dtype)
     _check(x, mode)
+
+
+@pytest.mark.parametrize("mode", ["head-wise", "token-wise", "head-wise-2pass"])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_signed_zeros_and_underflow(mode, dtype):
+    # -0.0 inputs (a 16-bit underflow of a small negative number) must encode as 0x80 like the reference's division
+    g = torch.Generator().manual_seed(77)
+    x = torch.randn((1, 2, 200, 128), generator=g)
+    x[0, 0, ::3, ::5] = -0.0
+    x[0, 1, 1::7, 3::11] = 0.0
+    x[0, 1, 5, :] = -1e-7   # flushes to -0 in fp16, stays a tiny normal in bf16
+    x[0, 0, 9, :] = torch.tensor(-6e-8)  # fp16 subnormal
+    _check(x.to(dtype), mode)
 
 
 @pytest.mark.parametrize("kind", ["outlier_channels", "huge_token", "zero_head"])
