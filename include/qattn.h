@@ -93,7 +93,9 @@ int qa_quantize_fp8(int n_tensors, const void* const* x, int x_dtype, const int6
  *   out         dense [B,Hq,Sq,D] of out_dtype (QA_DT_BF16 / QA_DT_FP16)
  *   lse         optional fp32 [B*Hq*Sq]: natural-log sum-exp of the scaled scores per row (for merging partial
  *               results across sequence shards); NULL to skip.  The reference leaves this output commented out
- *               (src/quantum_attn/tk/attention.py:333-346).
+ *               (src/quantum_attn/tk/attention.py:333-346).  In QA_P_E4M3 mode the sum is taken over the probabilities
+ *               as rounded to e4m3 - the weights that multiply V and normalise `out` - so it can differ from the
+ *               exact log-sum-exp by up to about 1e-2; merging partial results with it reproduces the one-launch result.
  *   sm_scale    softmax scale; pass 1/sqrt(D) for the reference's behaviour (src/quantum_attn/tk/attention.py:208-210)
  *   Hq % Hkv == 0 (GQA: kv head = q head / (Hq/Hkv)); D in {64, 128, 256}; causal mask is top-left aligned.
  */

@@ -19,13 +19,13 @@
 //   matters because at D = 128 the exp unit (MUFU, 16 / clk / SM), not the tensor pipe, bounds FP8 attention.
 //   To go past that bound a compile-time fraction of the exponentials is evaluated on the FMA pipe
 //   (Cody-Waite split + minimax polynomial, packed fp32x2 arithmetic) instead of MUFU.EX2.
-//   TMEM (512 columns): S_t at t*128 | P(t,b) at t*128 + 64 + b*32 | O_t at 256 + t*128.
+//   TMEM (512 columns): S_t at t*128 | P(t,b) at t*128 + 64 + b*32 | L_t at t*128 + 80 (row sums of P, single-e4m3
+//   mode) | O_t at 256 + t*128.
 //   K and V tiles are shared by both query tiles, halving L2->SMEM traffic per FLOP.
 //
 // Deliberately absent: any non-sm_100 path, any fallback.
 #pragma once
 #include <cmath>
-#include <cstdio>
 #include <type_traits>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -58,11 +58,8 @@ constexpr float kLog2e = 1.4426950408889634f;
 #ifndef QA_LOADQ
 #define QA_LOADQ 10    // S_{j+1} is pulled into registers after this many (of 16) quads of step j's exponentials
 #endif
-#ifndef QA_SWP
-#define QA_SWP 0       // software-pipeline depth of the exponentials, in quads (0: issue and consume in the same slot)
-#endif
-#ifndef QA_FENCEQ
-#define QA_FENCEQ 2    // a scheduling fence after every QA_FENCEQ-th quad
+#ifndef QA_MMASUM
+#define QA_MMASUM 1    // single-e4m3 P mode: row sums of P come from the tensor core (P x ones) instead of 64 FADDs per step
 #endif
 #ifndef QA_DECIDEQ
 #define QA_DECIDEQ 1   // quads of exponentials left when the rescale decision for the next step is taken
@@ -102,7 +99,13 @@ struct AttnCfg {
     // with 16-bit Q a query tile is as large as its output tile and dead once the tile's last MMA has retired (which
     // the epilogue waits for anyway): O is staged over Q
     static constexpr int SMEM_O = QK16_ ? SMEM_Q : ((NQ == 2) ? SMEM_V + STAGES * V_TILE : SMEM_K);
-    static constexpr int SMEM_BAR = (NQ == 2 && !QK16_) ? SMEM_O + NQ * O_TILE : SMEM_V + STAGES * V_TILE;
+    // single-e4m3 P mode: the row sums of P are accumulated by the tensor core, L (+)= P . 1, with a constant tile of
+    // e4m3 ones (0x38) as the B operand - every byte the MMA can touch holds the same value, so the tile's layout is
+    // immaterial - and a 16-column accumulator per query tile in the TMEM columns the 16-bit P buffers leave unused.
+    static constexpr bool MMASUM = (QA_MMASUM != 0) && (PMODE_ == QA_P_E4M3) && !QK16_;
+    static constexpr int ONES_BYTES = MMASUM ? 4096 : 0;  // 32 keys x one swizzle span
+    static constexpr int SMEM_ONES = (NQ == 2 && !QK16_) ? SMEM_O + NQ * O_TILE : SMEM_V + STAGES * V_TILE;
+    static constexpr int SMEM_BAR = SMEM_ONES + ONES_BYTES;
     static_assert(QK16_ || NQ == 2 || STAGES * K_TILE >= O_TILE, "K ring too small to stage O");
     static_assert(!QK16_ || Q_TILE == O_TILE, "O is staged over Q");
     static constexpr int SMEM_TOTAL = SMEM_BAR + 512 + 1024;  // + barriers + alignment slack
@@ -113,11 +116,13 @@ struct AttnCfg {
     static constexpr int TM_P = 64;                       // P(t, b) at t * 128 + 64 + b * 32
     static constexpr int TM_O = 256;                      // O_t at 256 + t * 128 (D <= 128), single O at D = 256
     static constexpr int TM_P_LO = 16;                    // hi/lo mode: second P tile 16 columns after the first
+    static constexpr int TM_L = 80;                       // MMASUM: L_t at t * 128 + 80 (16 columns, column 0 is read)
     // softmax range management: p' = 2^KOFF * exp2(s - m_used), m_used may lag the true max by <= TAU (log2 units)
     static constexpr float KOFF = V16 ? 0.f : 4.f;
     static constexpr float TAU = V16 ? 8.f : 4.f;
     // exponentials on the FMA pipe: polynomial degree (a single e4m3 P tolerates the quadratic's 1.7e-3)
-    static constexpr int POLY_NUM = QA_POLY_NUM;
+    // (with the row-sum FADDs gone the FMA pipe has room for one more polynomial pair in eight - measured on C2)
+    static constexpr int POLY_NUM = QA_POLY_NUM + (MMASUM ? 1 : 0);
     static constexpr int POLY_DEG = (PMODE_ == QA_P_E4M3) ? 2 : 3;
 };
 
@@ -134,7 +139,6 @@ struct AttnParams {
     float inv_group;  // Hkv / Hq
     long long* trace;  // developer builds (-DQA_TRACE): per-step clock64 stamps of one CTA, else unused
     int trace_x, trace_y;
-    int sched_fence;  // always 0: an opaque value for never-taken branches that keep ptxas from merging code regions
 };
 
 struct Barriers {
@@ -241,6 +245,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tma_prefetch_desc(&tmV);
         tma_prefetch_desc(&tmO);
     }
+    if constexpr (C::MMASUM) {
+        for (int i = threadIdx.x; i < C::ONES_BYTES / 4; i += C::NTHREADS)
+            reinterpret_cast<uint32_t*>(smem + C::SMEM_ONES)[i] = 0x38383838u;  // e4m3 1.0
+        fence_proxy_async_smem();  // the tensor core reads shared memory through the async proxy
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -296,6 +305,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             const uint32_t s_t = C::TM_S + t * 128;
             const uint32_t p_t0 = C::TM_P + t * 128;
             const uint32_t o_t = C::TM_O + (NQ == 2 ? t * 128 : 0);
+            const uint32_t l_t = C::TM_L + t * 128;
+            constexpr uint32_t idesc_l = make_idesc(0, 0, 0, 1, BM, 16);
+            const uint64_t ones_desc = make_smem_desc(smem_u32(smem + C::SMEM_ONES), C::V_BOX_BYTES, 8 * C::V_ROW, v_swz);
 
             // S_t = Q_t . K[64 keys]^T, the keys being rows [half * 64, half * 64 + 64) of K stage `stage`
             auto issue_qk = [&](int stage, int half) {
@@ -318,6 +330,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     if constexpr (!C::V16) {
                         umma_f8_ts(o_t, p_t + k * 8, bk, idesc_pv, (acc || k > 0) ? 1u : 0u);
                         if constexpr (C::PMODE == QA_P_E4M3_HILO) umma_f8_ts(o_t, p_t + C::TM_P_LO + k * 8, bk, idesc_pv, 1u);
+                        if constexpr (C::MMASUM) umma_f8_ts(l_t, p_t + k * 8, ones_desc, idesc_l, (acc || k > 0) ? 1u : 0u);
                     } else {
                         umma_f16_ts(o_t, p_t + k * 8, bk, idesc_pv, (acc || k > 0) ? 1u : 0u);
                     }
@@ -418,6 +431,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const uint32_t s_addr = tmem + lane_base + C::TM_S + t * 128;
         const uint32_t p_base = tmem + lane_base + C::TM_P + t * 128;
         const uint32_t o_addr = tmem + lane_base + C::TM_O + (NQ == 2 ? t * 128 : 0);
+        const uint32_t l_addr = tmem + lane_base + C::TM_L + t * 128;
         const int row_g = m0 + t * BM + row;
 
         float c;  // multiplier taking raw fp8 dot products to the base-2 softmax domain
@@ -486,6 +500,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 for (int i = 0; i < 32; ++i) o[i] *= alpha;
                 tmem_st_x32(o_addr + cc, o);
             }
+            if constexpr (C::MMASUM) {  // the row sum lives beside O and is rescaled with it
+                float lv = tmem_ld_x1(l_addr);
+                tmem_ld_wait();
+                tmem_st_x1(l_addr, lv * alpha);
+            }
             tmem_st_wait();
         };
 
@@ -500,9 +519,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         //   `need` (warp-uniform): some row of the warp has outgrown its stale maximum, as decided near the END of the
         //   previous step (see below) - so the common case enters the exponentials with nothing to wait for.
         auto step = [&](const int j, float (&s)[BS], float (&s_next)[BS], const float mx, bool& need, auto mask_tag,
-                        auto inst_tag, const bool last) -> float {
+                        const bool last) -> float {
             constexpr bool MASKED = decltype(mask_tag)::value;
-            constexpr int INST = decltype(inst_tag)::value;  // which copy of the step this is (distinct fence constants)
             QA_STAMP(t, j, 0);
             bool p_prev_pending = j > 0;  // P_{j-1} is stored but not yet published (see below)
             // lazy rescale: keep the stale max while the true max has grown by < 2^TAU
@@ -510,7 +528,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 const float m_new = fmaxf(m_used, mx);
                 const float alpha = ex2_approx((m_used - m_new) * c);  // 0 on the first step
                 m_used = m_new;
-                la.x *= alpha, la.y *= alpha, lb.x *= alpha, lb.y *= alpha;
+                if constexpr (!C::MMASUM) la.x *= alpha, la.y *= alpha, lb.x *= alpha, lb.y *= alpha;
                 if (j > 0) {
                     // O_t must be quiescent: PV_{j-1} is the only MMA that can still be writing it - and it cannot
                     // even start before P_{j-1} is published
@@ -536,25 +554,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 return make_float2(ex2_approx(x.x), ex2_approx(x.y));
             };
             uint32_t pw[C::V16 ? BS / 2 : BS / 4], pw_lo[C::PMODE == QA_P_E4M3_HILO ? BS / 4 : 1];
-            // Four columns per "quad".  The quad is software-pipelined by hand: quad i's exponentials are ISSUED (scale
-            // FFMA2 + MUFU.EX2, or the polynomial) in slot i and their results are CONSUMED (row sum, conversion to the P
-            // words) in slot i + SWP.  ptxas would otherwise sink all MUFUs of a basic block to its end, right in front
-            // of their consumers, and an in-order warp then alternates between an FMA-only stretch and a stall on the
-            // MUFU latency; a never-taken branch on an opaque kernel parameter after every slot keeps the slots apart.
-            constexpr int SWP = QA_SWP;
-            float2 pa[16], pb[16];
-            auto produce = [&](int i) {
-                pa[i] = exp_pair(2 * i);
-                pb[i] = exp_pair(2 * i + 1);
-            };
-            auto consume = [&](int i) {
-                const float2 p01 = pa[i], p23 = pb[i];
-#ifndef QA_EXP_NOSUM
-                la = __fadd2_rn(la, p01);
-                lb = __fadd2_rn(lb, p23);
-#else
-                if (i == 0) { la = __fadd2_rn(la, p01); lb = __fadd2_rn(lb, p23); }
-#endif
+            // four columns -> P words (and, unless the tensor core sums the rows of P, the running row sum)
+            auto exp_quad = [&](int i) {
+                const float2 p01 = exp_pair(2 * i), p23 = exp_pair(2 * i + 1);
+                if constexpr (!C::MMASUM) {
+                    la = __fadd2_rn(la, p01);
+                    lb = __fadd2_rn(lb, p23);
+                }
                 if constexpr (C::PMODE == QA_P_E4M3) {
                     pw[i] = pack_e4m3x4(p01.x, p01.y, p23.x, p23.y);
                 } else if constexpr (C::PMODE == QA_P_E4M3_HILO) {
@@ -566,36 +572,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     pw[2 * i] = p.out_fp16 ? pack_f16x2(p01.x, p01.y) : pack_bf16x2(p01.x, p01.y);
                     pw[2 * i + 1] = p.out_fp16 ? pack_f16x2(p23.x, p23.y) : pack_bf16x2(p23.x, p23.y);
                 }
-            };
-            // slot i; `extra` is other work that belongs into the same slot (a piece of the next row maximum)
-            auto exp_slot = [&](int i, auto extra) {
-#ifdef QA_EXP_LONE
-                if constexpr (decltype(mask_tag)::value) { pw[C::V16 ? 2 * i : i] = 0; extra(); return; }
-#endif
-                if (SWP > 0 && (i % QA_FENCEQ) == QA_FENCEQ - 1) {
-                    // the slot is the body of a do-while whose back edge is never taken (p.sched_fence is always 0,
-                    // which ptxas cannot know): a basic block of its own, at the price of a compare and a
-                    // fall-through branch
-                    int never;
-                    do {
-                        produce(i);
-                        if (i >= SWP) consume(i - SWP);
-                        extra();
-                        asm volatile("mov.b32 %0, %1;" : "=r"(never) : "r"(p.sched_fence));
-                    } while (__builtin_expect(never == i + 1 + 16 * INST, 0));
-                } else {
-                    produce(i);
-                    if (i >= SWP) consume(i - SWP);
-                    extra();
-                }
-            };
-            auto exp_quad = [&](int i) { exp_slot(i, [] {}); };
-            auto exp_drain = [&]() {  // results of the last SWP quads
-#ifdef QA_EXP_LONE
-                if constexpr (decltype(mask_tag)::value) return;
-#endif
-#pragma unroll
-                for (int i = 16 - SWP; i < 16; ++i) consume(i);
             };
 
 #pragma unroll
@@ -631,23 +607,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 constexpr int PER = (4 + REST - 1) / REST;    // pieces per quad
 #pragma unroll
                 for (int i = LOADQ + 2; i < 16 - DECQ; ++i) {
-                    exp_slot(i, [&] {
+                    exp_quad(i);
 #pragma unroll
-                        for (int q = 0; q < PER; ++q) {
-                            const int piece = (i - LOADQ - 2) * PER + q;
-                            if (piece < 4) max16(s_next, piece, ma, mb);
-                        }
-                    });
+                    for (int q = 0; q < PER; ++q) {
+                        const int piece = (i - LOADQ - 2) * PER + q;
+                        if (piece < 4) max16(s_next, piece, ma, mb);
+                    }
                 }
                 need = __any_sync(0xffffffffu, (fmaxf(ma, mb) - m_used) * c > C::TAU);
 #pragma unroll
                 for (int i = 16 - DECQ; i < 16; ++i) exp_quad(i);
-                exp_drain();
             } else {
                 need = false;
 #pragma unroll
                 for (int i = LOADQ; i < 16; ++i) exp_quad(i);
-                exp_drain();
                 // P buffer reuse: PV_{j-2} must have drained it.  Seeing S_{j+1} (issued after PV_{j-2}, in-order
                 // tensor pipe) proves that in every other step; the last one waits for PV_{j-1} explicitly.
                 if (j >= 2) mbar_wait(&bars->pv_done[t][(j - 1) & 1], ((j - 1) >> 1) & 1);
@@ -699,32 +672,32 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             using std::false_type;
             using std::true_type;
             // main loop: steps whose successor exists and needs no mask, two per trip (the score registers ping-pong)
-#ifdef QA_EXP_LONE  // experiment: tile 1 skips its exponentials (it runs the masked instance only, which is stubbed)
-            const int n_fast = t == 1 ? 0 : min(my_steps - 1, j_mask - 1);
-#else
             const int n_fast = min(my_steps - 1, j_mask - 1);
-#endif
             int j = 0;
             bool need = true;  // first step: m_used = -inf
             for (; j + 2 <= n_fast; j += 2) {
-                mx = step(j, s_a, s_b, mx, need, false_type{}, std::integral_constant<int, 0>{}, false);
-                mx = step(j + 1, s_b, s_a, mx, need, false_type{}, std::integral_constant<int, 1>{}, false);
+                mx = step(j, s_a, s_b, mx, need, false_type{}, false);
+                mx = step(j + 1, s_b, s_a, mx, need, false_type{}, false);
             }
             // tail: the few steps around the causal diagonal / ragged end, and the last one (rolled, one instance)
 #pragma unroll 1
             for (; j < my_steps; ++j) {
-                mx = step(j, s_a, s_b, mx, need, true_type{}, std::integral_constant<int, 2>{}, j + 1 == my_steps);
+                mx = step(j, s_a, s_b, mx, need, true_type{}, j + 1 == my_steps);
 #pragma unroll
                 for (int i = 0; i < BS; ++i) s_a[i] = s_b[i];
             }
         }
-        const float l = (la.x + la.y) + (lb.x + lb.y);
+        float l = (la.x + la.y) + (lb.x + lb.y);
         QA_STAMP(t, 78, 3);
 
         // ---------------------------------------------------------------- epilogue: O / l -> 16 bit -> smem -> TMA
         mbar_wait(&bars->o_full[t], 0);
         tc_fence_after();
         QA_STAMP(t, 78, 4);
+        if constexpr (C::MMASUM) {
+            l = tmem_ld_x1(l_addr);
+            tmem_ld_wait();
+        }
         const float sv = C::V16 ? 1.f : p.scale_v[bhkv];
         const float inv = __fdividef(sv, l);
         uint8_t* o_smem = smem + C::SMEM_O + t * C::O_TILE;
@@ -814,7 +787,6 @@ static int launch_cfg(const AttnArgs& a, cudaStream_t stream, int* launches) {
     p.trace = nullptr;
     p.trace_x = p.trace_y = 0;
 #endif
-    p.sched_fence = 0;
 
     auto kern = attn_fwd_kernel<C, CAUSAL, TOKEN>;
     static bool attr_done = false;  // per instantiation; racing threads set the same value

@@ -91,7 +91,10 @@ def test_key_blocks_plus_merge_equal_one_launch(pv):
                                     return_lse=True, **kw)
         _native.merge_partials(o_acc, lse_acc, o, l, first=(i == 0), out=out if b == S else None)
     torch.cuda.synchronize()
-    assert torch.allclose(lse_acc, lse_full, atol=2e-3), (lse_acc - lse_full).abs().max()
+    # single-e4m3 mode: l is the row sum of the QUANTISED probabilities (accumulated by the tensor core, the same
+    # weights that normalise O), and how a probability rounds depends on the block's own running maximum
+    lse_tol = 1e-2 if pv == "fp8" else 2e-3
+    assert torch.allclose(lse_acc, lse_full, atol=lse_tol), (lse_acc - lse_full).abs().max()
     ref = oracle.fp8_attention_ref(q8.view(torch.uint8).cpu().numpy(), k8.view(torch.uint8).cpu().numpy(),
                                    v8.view(torch.uint8).cpu().numpy(), sq.cpu().numpy(), sk.cpu().numpy(),
                                    scale_v=sv.cpu().numpy())
@@ -104,7 +107,7 @@ def test_key_blocks_plus_merge_equal_one_launch(pv):
     _, lse_ref = oracle.attention_block_ref(q8.view(torch.uint8).cpu().numpy(), k8.view(torch.uint8).cpu().numpy(),
                                             v8.view(torch.uint8).cpu().numpy(), sq.cpu().numpy(), sk.cpu().numpy(),
                                             sv.cpu().numpy())
-    assert torch.allclose(lse_full.cpu().double(), lse_ref, atol=2e-3)
+    assert torch.allclose(lse_full.cpu().double(), lse_ref, atol=lse_tol)
 
 
 def test_ring_single_rank_is_fp8_attn_func():
