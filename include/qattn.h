@@ -90,7 +90,7 @@ int qa_quantize_fp8(int n_tensors, const void* const* x, int x_dtype, const int6
  *   v           QA_P_E4M3 / QA_P_E4M3_HILO: dense e4m3 [B,Hkv,Skv,D] with scale_v[B*Hkv] (head-wise)
  *               QA_P_16BIT: dense bf16/fp16 (v_dtype) [B,Hkv,Skv,D], scale_v may be NULL
  *   scale_q/k   fp32, layout per scale_mode (token mode: scale_q[B*Hq*Sq], scale_k[B*Hkv*Skv])
- *   out         dense [B,Hq,Sq,D] of out_dtype (QA_DT_BF16 / QA_DT_FP16)
+ *   out         dense [B,Hq,Sq,D] of out_dtype (QA_DT_BF16 / QA_DT_FP16), 32-byte aligned
  *   lse         optional fp32 [B*Hq*Sq]: natural-log sum-exp of the scaled scores per row (for merging partial
  *               results across sequence shards); NULL to skip.  The reference leaves this output commented out
  *               (src/quantum_attn/tk/attention.py:333-346).  In QA_P_E4M3 mode the sum is taken over the probabilities

@@ -139,9 +139,9 @@ int qa_fp8_attn_fwd(const void* q8, const void* k8, const void* v, int v_dtype, 
     } else {
         return set_error(QA_ERR_INVALID, "unknown p_mode %d", p_mode);
     }
-    if ((reinterpret_cast<uintptr_t>(q8) | reinterpret_cast<uintptr_t>(k8) | reinterpret_cast<uintptr_t>(v) |
-         reinterpret_cast<uintptr_t>(out)) & 15)
+    if ((reinterpret_cast<uintptr_t>(q8) | reinterpret_cast<uintptr_t>(k8) | reinterpret_cast<uintptr_t>(v)) & 15)
         return set_error(QA_ERR_INVALID, "tensor base pointers must be 16-byte aligned");
+    if (reinterpret_cast<uintptr_t>(out) & 31) return set_error(QA_ERR_INVALID, "out must be 32-byte aligned");
     int rc = check_device();
     if (rc != QA_OK) return rc;
     AttnArgs a;
@@ -171,9 +171,9 @@ int qa_attn_fwd(const void* q, const void* k, const void* v, int dtype, void* ou
         return set_error(QA_ERR_INVALID, "Expect Hq to be a multiple of Hkv but got Hq=%d and Hkv=%d.", Hq, Hkv);
     if (Hq > 65535 || B > 65535) return set_error(QA_ERR_INVALID, "B or Hq exceeds the grid limit 65535");
     if (!(sm_scale > 0.f) || !(sm_scale < 1e30f)) return set_error(QA_ERR_INVALID, "sm_scale must be positive");
-    if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
-         reinterpret_cast<uintptr_t>(out)) & 15)
+    if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v)) & 15)
         return set_error(QA_ERR_INVALID, "tensor base pointers must be 16-byte aligned");
+    if (reinterpret_cast<uintptr_t>(out) & 31) return set_error(QA_ERR_INVALID, "out must be 32-byte aligned");
     int rc = check_device();
     if (rc != QA_OK) return rc;
     AttnArgs a;

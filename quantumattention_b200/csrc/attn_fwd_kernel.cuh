@@ -61,6 +61,9 @@ constexpr float kLog2e = 1.4426950408889634f;
 #ifndef QA_MMASUM
 #define QA_MMASUM 1    // single-e4m3 P mode: row sums of P come from the tensor core (P x ones) instead of 64 FADDs per step
 #endif
+#ifndef QA_DIRECT_STORE
+#define QA_DIRECT_STORE 1  // epilogue writes O rows straight from registers (256-bit stores) instead of smem + TMA
+#endif
 #ifndef QA_DECIDEQ
 #define QA_DECIDEQ 1   // quads of exponentials left when the rescale decision for the next step is taken
 #endif
@@ -89,25 +92,27 @@ struct AttnCfg {
     static constexpr int V_TILE = BN * D_ * VB;
     static constexpr int O_BOXES = D_ / 64;  // 16-bit output, 64 elements = 128 bytes per box row
     static constexpr int O_TILE = BM * D_ * 2;
+    static constexpr bool DIRECT_STORE = (QA_DIRECT_STORE != 0);
     static constexpr int STAGES = QK16_ ? (D_ == 64 ? 4 : (D_ == 128 ? 2 : 1))
-                                        : ((D_ == 64) ? 4 : (D_ == 128 ? (V16 ? 2 : 3) : 2));
+                                        : ((D_ == 64) ? 4 : (D_ == 128 ? ((V16 && !DIRECT_STORE) ? 2 : 3) : 2));
     static constexpr int SMEM_Q = 0;
     static constexpr int SMEM_K = SMEM_Q + NQ * Q_TILE;
     static constexpr int SMEM_V = SMEM_K + STAGES * K_TILE;
-    // O staging for the TMA store: its own region when two query tiles finish at different times; with a single
-    // tile (D = 256) every MMA has retired before the epilogue, so the dead K ring is reused
-    // with 16-bit Q a query tile is as large as its output tile and dead once the tile's last MMA has retired (which
-    // the epilogue waits for anyway): O is staged over Q
-    static constexpr int SMEM_O = QK16_ ? SMEM_Q : ((NQ == 2) ? SMEM_V + STAGES * V_TILE : SMEM_K);
+    // O staging for the TMA-store epilogue (QA_DIRECT_STORE=0 only; the default epilogue stores rows from registers):
+    // its own region when two query tiles finish at different times; with a single tile (D = 256) every MMA has retired
+    // before the epilogue, so the dead K ring is reused; with 16-bit Q a query tile is as large as its output tile and
+    // dead once the tile's last MMA has retired, so O is staged over Q
+    static constexpr bool O_OWN = !DIRECT_STORE && NQ == 2 && !QK16_;
+    static constexpr int SMEM_O = QK16_ ? SMEM_Q : (O_OWN ? SMEM_V + STAGES * V_TILE : SMEM_K);
+    static_assert(DIRECT_STORE || QK16_ || NQ == 2 || STAGES * K_TILE >= O_TILE, "K ring too small to stage O");
+    static_assert(!QK16_ || Q_TILE == O_TILE, "O is staged over Q");
     // single-e4m3 P mode: the row sums of P are accumulated by the tensor core, L (+)= P . 1, with a constant tile of
     // e4m3 ones (0x38) as the B operand - every byte the MMA can touch holds the same value, so the tile's layout is
     // immaterial - and a 16-column accumulator per query tile in the TMEM columns the 16-bit P buffers leave unused.
     static constexpr bool MMASUM = (QA_MMASUM != 0) && (PMODE_ == QA_P_E4M3) && !QK16_;
     static constexpr int ONES_BYTES = MMASUM ? 4096 : 0;  // 32 keys x one swizzle span
-    static constexpr int SMEM_ONES = (NQ == 2 && !QK16_) ? SMEM_O + NQ * O_TILE : SMEM_V + STAGES * V_TILE;
+    static constexpr int SMEM_ONES = O_OWN ? SMEM_O + NQ * O_TILE : SMEM_V + STAGES * V_TILE;
     static constexpr int SMEM_BAR = SMEM_ONES + ONES_BYTES;
-    static_assert(QK16_ || NQ == 2 || STAGES * K_TILE >= O_TILE, "K ring too small to stage O");
-    static_assert(!QK16_ || Q_TILE == O_TILE, "O is staged over Q");
     static constexpr int SMEM_TOTAL = SMEM_BAR + 512 + 1024;  // + barriers + alignment slack
     static_assert(SMEM_TOTAL <= 232448, "shared memory budget exceeded");
     static constexpr int NTHREADS = (NQ * 4 + 4) * 32;  // softmax warpgroups + one warpgroup holding the MMA / TMA warps
@@ -131,6 +136,7 @@ struct AttnParams {
     const float* scale_k;
     const float* scale_v;
     float* lse;
+    void* out;  // dense [B, Hq, Sq, D], 16 bit
     int B, Hq, Hkv, Sq, Skv;
     int causal;
     float sm_scale_log2;  // sm_scale * log2(e)
@@ -226,24 +232,59 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     if (warp == 1) {  // one barrier per lane
         if (lane < 4) {
             const int t = lane >> 1, x = lane & 1;
-            mbar_init(x ? &bars->o_full[t] : &bars->q_full[t], 1);
+            if (x) mbar_init(&bars->o_full[t], 1);
             mbar_init(&bars->pv_done[t][x], 1);
             mbar_init(&bars->p_full[t][x], 128);
             mbar_init(x ? &bars->s_free[t] : &bars->s_full[t], x ? 128 : 1);
-        } else if (lane < 8) {
-            const int st = lane - 4;
-            mbar_init(&bars->k_full[st], 1);
-            mbar_init(&bars->k_empty[st], NQ);  // released by every tile's MMA warp
-            mbar_init(&bars->v_full[st], 1);
-            mbar_init(&bars->v_empty[st], NQ);
         }
         fence_barrier_init();
     }
-    if (warp == NQ * 4 + 1 && lane == 0) {
-        tma_prefetch_desc(&tmQ);
-        tma_prefetch_desc(&tmK);
-        tma_prefetch_desc(&tmV);
-        tma_prefetch_desc(&tmO);
+    // The TMA producer initialises its own barriers and starts Q and the first K / V tiles right away: their flight
+    // time (about as long as the rest of the setup - TMEM allocation, the CTA-wide barrier) is then off the critical path.
+    const int n_pre = min(n_kv, C::STAGES);
+    auto load_kv = [&](int n) {
+        const int s = n % C::STAGES;
+        mbar_arrive_expect_tx(&bars->k_full[s], C::K_TILE);
+        for (int x = 0; x < C::QK_BOXES; ++x)
+            tma_load_3d(smem + C::SMEM_K + s * C::K_TILE + x * C::QK_BOX_BYTES, &tmK, &bars->k_full[s],
+                        x * (C::QK_ROW / C::QB), n * BN, bhkv, kEvictLast);
+    };
+    auto load_v = [&](int n) {
+        const int s = n % C::STAGES;
+        mbar_arrive_expect_tx(&bars->v_full[s], C::V_TILE);
+        for (int x = 0; x < C::V_BOXES; ++x)
+            tma_load_3d(smem + C::SMEM_V + s * C::V_TILE + x * C::V_BOX_BYTES, &tmV, &bars->v_full[s],
+                        x * (C::V_ROW / C::VB), n * BN, bhkv, kEvictLast);
+    };
+    if (warp == NQ * 4 + 1) {
+        if (lane < 4) {
+            mbar_init(&bars->k_full[lane], 1);
+            mbar_init(&bars->k_empty[lane], NQ);  // released by every tile's MMA warp
+            mbar_init(&bars->v_full[lane], 1);
+            mbar_init(&bars->v_empty[lane], NQ);
+        } else if (lane < 4 + NQ) {
+            mbar_init(&bars->q_full[lane - 4], 1);
+        }
+        fence_barrier_init();
+        __syncwarp();
+        if (lane == 0) {
+            tma_prefetch_desc(&tmQ);
+            tma_prefetch_desc(&tmK);
+            tma_prefetch_desc(&tmV);
+            tma_prefetch_desc(&tmO);
+            for (int t = 0; t < NQ; ++t) {
+                mbar_arrive_expect_tx(&bars->q_full[t], C::Q_TILE);
+                for (int x = 0; x < C::QK_BOXES; ++x)
+                    tma_load_3d(smem + C::SMEM_Q + t * C::Q_TILE + x * C::QK_BOX_BYTES, &tmQ, &bars->q_full[t],
+                                x * (C::QK_ROW / C::QB), m0 + t * BM, bh, kEvictFirst);
+                if (t == 0) load_kv(0);  // K tile 0 right behind the first Q tile: S_0 needs exactly these two
+            }
+            load_v(0);
+            for (int n = 1; n < n_pre; ++n) {
+                load_kv(n);
+                load_v(n);
+            }
+        }
     }
     if constexpr (C::MMASUM) {
         for (int i = threadIdx.x; i < C::ONES_BYTES / 4; i += C::NTHREADS)
@@ -263,25 +304,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (warp == NQ * 4 + 1) {
             // =========================================================== TMA producer
             if (lane == 0) {
-                for (int t = 0; t < NQ; ++t) {
-                    mbar_arrive_expect_tx(&bars->q_full[t], C::Q_TILE);
-                    for (int x = 0; x < C::QK_BOXES; ++x)
-                        tma_load_3d(smem + C::SMEM_Q + t * C::Q_TILE + x * C::QK_BOX_BYTES, &tmQ, &bars->q_full[t],
-                                    x * (C::QK_ROW / C::QB), m0 + t * BM, bh, kEvictFirst);
-                }
-                for (int n = 0; n < n_kv; ++n) {
+                for (int n = n_pre; n < n_kv; ++n) {  // (Q and the first n_pre tiles were issued during the setup)
                     const int s = n % C::STAGES;
                     const uint32_t ph = (n / C::STAGES) & 1;
                     mbar_wait(&bars->k_empty[s], ph ^ 1);
-                    mbar_arrive_expect_tx(&bars->k_full[s], C::K_TILE);
-                    for (int x = 0; x < C::QK_BOXES; ++x)
-                        tma_load_3d(smem + C::SMEM_K + s * C::K_TILE + x * C::QK_BOX_BYTES, &tmK, &bars->k_full[s],
-                                    x * (C::QK_ROW / C::QB), n * BN, bhkv, kEvictLast);
+                    load_kv(n);
                     mbar_wait(&bars->v_empty[s], ph ^ 1);
-                    mbar_arrive_expect_tx(&bars->v_full[s], C::V_TILE);
-                    for (int x = 0; x < C::V_BOXES; ++x)
-                        tma_load_3d(smem + C::SMEM_V + s * C::V_TILE + x * C::V_BOX_BYTES, &tmV, &bars->v_full[s],
-                                    x * (C::V_ROW / C::VB), n * BN, bhkv, kEvictLast);
+                    load_v(n);
                 }
             }
         } else if (warp == NQ * 4 || (NQ == 2 && warp == NQ * 4 + 2)) {
@@ -700,6 +729,30 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         const float sv = C::V16 ? 1.f : p.scale_v[bhkv];
         const float inv = __fdividef(sv, l);
+#if QA_DIRECT_STORE
+        // A thread owns a whole output row (D * 2 contiguous bytes): it writes it straight from its registers, one
+        // 32-byte sector per store.  Nothing to stage, fence or wait for - the CTA is free to retire as soon as the
+        // stores are issued, where the shared-memory + TMA route kept it alive until the bulk store had read the tile.
+        uint8_t* o_row = static_cast<uint8_t*>(p.out) + (size_t(bh) * p.Sq + min(row_g, p.Sq - 1)) * (D * 2);
+#pragma unroll
+        for (int cc = 0; cc < D; cc += 32) {
+            float o[32];
+            tmem_ld_x32(o_addr + cc, o);
+            tmem_ld_wait();
+            uint32_t w[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float a = o[2 * i] * inv, bb = o[2 * i + 1] * inv;
+                w[i] = p.out_fp16 ? pack_f16x2(a, bb) : pack_bf16x2(a, bb);
+            }
+            if (row_g < p.Sq) {
+                st_global_32B(o_row + cc * 2, w);
+                st_global_32B(o_row + cc * 2 + 32, w + 8);
+            }
+        }
+        if (p.lse != nullptr && row_g < p.Sq)
+            p.lse[size_t(bh) * p.Sq + row_g] = (m_used * c + (__log2f(l) - C::KOFF)) * 0.6931471805599453f;
+#else
         uint8_t* o_smem = smem + C::SMEM_O + t * C::O_TILE;
 #pragma unroll
         for (int cc = 0; cc < D; cc += 32) {
@@ -730,6 +783,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             tma_store_commit();
             tma_store_wait_read<0>();  // the CTA only has to keep its shared memory alive until it has been read
         }
+#endif
         QA_STAMP(t, 78, 5);
     }
 
@@ -774,6 +828,7 @@ static int launch_cfg(const AttnArgs& a, cudaStream_t stream, int* launches) {
     p.scale_k = a.scale_k;
     p.scale_v = a.scale_v;
     p.lse = a.lse;
+    p.out = a.out;
     p.B = a.B, p.Hq = a.Hq, p.Hkv = a.Hkv, p.Sq = a.Sq, p.Skv = a.Skv;
     p.causal = a.causal;
     p.sm_scale_log2 = a.sm_scale * kLog2e;

@@ -317,6 +317,12 @@ __device__ __forceinline__ void tmem_st_u8(uint32_t taddr, const uint32_t* r) {
                  : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                  : "memory");
 }
+// one full 32-byte sector from registers (sm_100: 256-bit global stores)
+__device__ __forceinline__ void st_global_32B(void* ptr, const uint32_t* w) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+                 "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                 : "memory");
+}
 // one column (one fp32 per lane)
 __device__ __forceinline__ float tmem_ld_x1(uint32_t taddr) {
     float r;
