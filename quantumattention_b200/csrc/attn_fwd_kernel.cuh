@@ -56,13 +56,22 @@ constexpr float kLog2e = 1.4426950408889634f;
 #define QA_POLY_NUM 2  // of every 8 pairs of exponentials, how many run on the FMA pipe instead of MUFU
 #endif
 #ifndef QA_LOADQ
-#define QA_LOADQ 10    // S_{j+1} is pulled into registers after this many (of 16) quads of step j's exponentials
+#define QA_LOADQ 8    // S_{j+1} is pulled into registers after this many (of 16) quads of step j's exponentials
 #endif
 #ifndef QA_MMASUM
 #define QA_MMASUM 1    // single-e4m3 P mode: row sums of P come from the tensor core (P x ones) instead of 64 FADDs per step
 #endif
 #ifndef QA_DIRECT_STORE
 #define QA_DIRECT_STORE 1  // epilogue writes O rows straight from registers (256-bit stores) instead of smem + TMA
+#endif
+#ifndef QA_PUBQ
+#define QA_PUBQ 2      // P_{j-1} (stored at the end of step j-1) is published after this many quads of step j
+#endif
+#ifndef QA_LDWAITQ
+#define QA_LDWAITQ 4   // quads of exponentials between the TMEM load of S_{j+1} and the wait for it
+#endif
+#ifndef QA_PROBEQ
+#define QA_PROBEQ 0    // > 0: the barrier of S_{j+1} is probed this many quads before the load (hides the probe's latency)
 #endif
 #ifndef QA_DECIDEQ
 #define QA_DECIDEQ 1   // quads of exponentials left when the rescale decision for the next step is taken
@@ -603,24 +612,33 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 }
             };
 
+            constexpr int PUBQ = QA_PUBQ, LDW = QA_LDWAITQ, PROBEQ = QA_PROBEQ;
+            static_assert(PUBQ >= 1 && PUBQ <= LOADQ - PROBEQ && LDW >= 1, "quad schedule");
 #pragma unroll
-            for (int i = 0; i < 2; ++i) exp_quad(i);
+            for (int i = 0; i < PUBQ; ++i) exp_quad(i);
             if (p_prev_pending) {  // P_{j-1} was stored at the end of the previous step: publish it now
                 tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(&bars->p_full[t][(j - 1) & 1]);
             }
 #pragma unroll
-            for (int i = 2; i < LOADQ; ++i) exp_quad(i);
+            for (int i = PUBQ; i < LOADQ - PROBEQ; ++i) exp_quad(i);
             float ma = -INFINITY, mb = -INFINITY;
             if (!last) {
                 // S_{j+1} was issued by the tensor core when this thread released S_j, about one step ago
-                mbar_wait(&bars->s_full[t], (j + 1) & 1);
+                bool s_ready = false;
+                if constexpr (PROBEQ > 0) {
+                    s_ready = mbar_test_wait(&bars->s_full[t], (j + 1) & 1);
+#pragma unroll
+                    for (int i = LOADQ - PROBEQ; i < LOADQ; ++i) exp_quad(i);
+                }
+                QA_STAMP(t, j, 5);
+                if (!s_ready) mbar_wait(&bars->s_full[t], (j + 1) & 1);
                 tc_fence_after();
                 tmem_ld_f64(s_addr, s_next);
                 QA_STAMP(t, j, 2);
 #pragma unroll
-                for (int i = LOADQ; i < LOADQ + 2; ++i) exp_quad(i);
+                for (int i = LOADQ; i < LOADQ + LDW; ++i) exp_quad(i);
                 tmem_ld_wait();
                 tc_fence_before();
                 mbar_arrive(&bars->s_free[t]);  // the score buffer may be overwritten by QK_{j+2}
@@ -631,15 +649,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 // pieces in all; the rescale decision for step j + 1 (a warp vote) is taken before those last quads, whose
                 // exponentials hide its latency
                 constexpr int DECQ = QA_DECIDEQ;
-                constexpr int REST = 14 - LOADQ - DECQ;       // quads carrying a piece of the maximum
+                constexpr int REST = 16 - LDW - LOADQ - DECQ;  // quads carrying a piece of the maximum
                 static_assert(REST >= 1, "LOADQ / QA_DECIDEQ leave no room for the row maximum");
                 constexpr int PER = (4 + REST - 1) / REST;    // pieces per quad
 #pragma unroll
-                for (int i = LOADQ + 2; i < 16 - DECQ; ++i) {
+                for (int i = LOADQ + LDW; i < 16 - DECQ; ++i) {
                     exp_quad(i);
 #pragma unroll
                     for (int q = 0; q < PER; ++q) {
-                        const int piece = (i - LOADQ - 2) * PER + q;
+                        const int piece = (i - LOADQ - LDW) * PER + q;
                         if (piece < 4) max16(s_next, piece, ma, mb);
                     }
                 }
@@ -649,7 +667,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             } else {
                 need = false;
 #pragma unroll
-                for (int i = LOADQ; i < 16; ++i) exp_quad(i);
+                for (int i = LOADQ - PROBEQ; i < 16; ++i) exp_quad(i);
                 // P buffer reuse: PV_{j-2} must have drained it.  Seeing S_{j+1} (issued after PV_{j-2}, in-order
                 // tensor pipe) proves that in every other step; the last one waits for PV_{j-1} explicitly.
                 if (j >= 2) mbar_wait(&bars->pv_done[t][(j - 1) & 1], ((j - 1) >> 1) & 1);

@@ -24,7 +24,7 @@ print("step | sm0: top ldwait maxdone arrive end nr | sm1: ... | mma0: waitP got
 for j in range(int(sys.argv[1]) if len(sys.argv) > 1 else 30):
     row = []
     for r in (0, 1):
-        row.append(" ".join(f"{rel(t[r, j, e]):6d}" for e in range(5)) + f" {int(t[r, j, 5])}")
+        row.append(" ".join(f"{rel(t[r, j, e]):6d}" for e in range(5)) + f" {rel(t[r, j, 2]) - rel(t[r, j, 5])}")
     for r in (2, 3):
         row.append(" ".join(f"{rel(t[r, j, e]):6d}" for e in range(3)))
     print(f"{j:3d} | " + " | ".join(row))
@@ -32,7 +32,8 @@ for r, name in ((0, "sm0"), (1, "sm1")):
     d = t[r, 8:60]
     print(name, "mean step", float((d[1:, 0] - d[:-1, 0]).float().mean()), "ldwait", float((d[:, 1] - d[:, 0]).float().mean()),
           "max", float((d[:, 2] - d[:, 1]).float().mean()), "exp", float((d[:, 3] - d[:, 2]).float().mean()),
-          "post", float((d[:, 4] - d[:, 3]).float().mean()), "next_ready frac", float(d[:, 5].float().mean()))
+          "post", float((d[:, 4] - d[:, 3]).float().mean()),
+          "wait for S_{j+1}: even steps", float((d[0::2, 2] - d[0::2, 5]).float().mean()), "odd steps", float((d[1::2, 2] - d[1::2, 5]).float().mean()))
 for r, name in ((2, "mma0"), (3, "mma1")):
     d = t[r, 8:60]
     print(name, "waitP", float((d[:, 1] - d[:, 0]).float().mean()), "issue", float((d[:, 2] - d[:, 1]).float().mean()))
