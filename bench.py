@@ -169,7 +169,17 @@ def fp8_gemm_peak(device):
         return None
 
 
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version line on the first
+    collective): point file descriptor 1 at stderr for the duration of the run and keep the real stdout for the line."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
+    out = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)
@@ -217,7 +227,7 @@ def main():
             "e2e": {"value": leg["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), file=out, flush=True)
         return
 
     # ------------------------------------------------------------------------------ our arm (B200)
@@ -462,7 +472,7 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         leg = cpu_reference_leg(args.workload)
         line["cpu_baseline"] = {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")}
-    print(json.dumps(line))
+    print(json.dumps(line), file=out, flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
