@@ -73,6 +73,9 @@ constexpr float kLog2e = 1.4426950408889634f;
 #ifndef QA_PROBEQ
 #define QA_PROBEQ 0    // > 0: the barrier of S_{j+1} is probed this many quads before the load (hides the probe's latency)
 #endif
+#ifndef QA_SOLO
+#define QA_SOLO 0      // 1: one query tile per CTA and two CTAs per SM for D <= 128 (see AttnCfg::SOLO)
+#endif
 #ifndef QA_DECIDEQ
 #define QA_DECIDEQ 1   // quads of exponentials left when the rescale decision for the next step is taken
 #endif
@@ -86,7 +89,16 @@ struct AttnCfg {
     static constexpr bool QK16 = QK16_;
     static constexpr bool V16 = (PMODE_ == QA_P_16BIT);
     static_assert(!QK16_ || V16, "16-bit Q/K go with 16-bit P and V");
-    static constexpr int NQ = (D_ <= 128) ? 2 : 1;  // O for two tiles does not fit TMEM at D = 256
+    // Two shapes of CTA.  PAIR: two query tiles share the K / V tiles of one CTA (one CTA per SM, all 512 TMEM columns).
+    // SOLO (-DQA_SOLO=1, D <= 128, 8-bit Q/K/V): one query tile per CTA, 256 TMEM columns, two CTAs per SM - each tile
+    // loads its own K / V, but one CTA's prologue / epilogue overlaps the other's main loop and causal work is dealt out
+    // in 128-row units.
+    static constexpr bool SOLO = (QA_SOLO != 0) && D_ <= 128 && !QK16_ && !(PMODE_ == QA_P_16BIT);
+    static constexpr int NQ = (D_ <= 128 && !SOLO) ? 2 : 1;  // O for two tiles does not fit TMEM at D = 256
+    static constexpr int CTAS_PER_SM = SOLO ? 2 : 1;
+    static constexpr int TMEM_COLS = SOLO ? 256 : 512;
+    static constexpr bool REBALANCE = (NQ == 2) || SOLO;  // setmaxnreg: registers move to the softmax warps
+    static constexpr int REG_SOFTMAX = SOLO ? 216 : 224, REG_OTHER = SOLO ? 40 : 56;
     static constexpr int VB = V16 ? 2 : 1;          // bytes per V element
     static constexpr int QB = QK16_ ? 2 : 1;        // bytes per Q / K element
     // shared-memory tiles are stored as "boxes" whose rows are one swizzle span (<= 128 bytes) wide
@@ -102,8 +114,9 @@ struct AttnCfg {
     static constexpr int O_BOXES = D_ / 64;  // 16-bit output, 64 elements = 128 bytes per box row
     static constexpr int O_TILE = BM * D_ * 2;
     static constexpr bool DIRECT_STORE = (QA_DIRECT_STORE != 0);
-    static constexpr int STAGES = QK16_ ? (D_ == 64 ? 4 : (D_ == 128 ? 2 : 1))
-                                        : ((D_ == 64) ? 4 : (D_ == 128 ? ((V16 && !DIRECT_STORE) ? 2 : 3) : 2));
+    static constexpr int STAGES = SOLO ? (D_ == 64 ? 4 : 2)
+                                  : QK16_ ? (D_ == 64 ? 4 : (D_ == 128 ? 2 : 1))
+                                          : ((D_ == 64) ? 4 : (D_ == 128 ? ((V16 && !DIRECT_STORE) ? 2 : 3) : 2));
     static constexpr int SMEM_Q = 0;
     static constexpr int SMEM_K = SMEM_Q + NQ * Q_TILE;
     static constexpr int SMEM_V = SMEM_K + STAGES * K_TILE;
@@ -123,12 +136,12 @@ struct AttnCfg {
     static constexpr int SMEM_ONES = O_OWN ? SMEM_O + NQ * O_TILE : SMEM_V + STAGES * V_TILE;
     static constexpr int SMEM_BAR = SMEM_ONES + ONES_BYTES;
     static constexpr int SMEM_TOTAL = SMEM_BAR + 512 + 1024;  // + barriers + alignment slack
-    static_assert(SMEM_TOTAL <= 232448, "shared memory budget exceeded");
+    static_assert(SMEM_TOTAL * CTAS_PER_SM + 1024 * CTAS_PER_SM <= 233472, "shared memory budget exceeded");
     static constexpr int NTHREADS = (NQ * 4 + 4) * 32;  // softmax warpgroups + one warpgroup holding the MMA / TMA warps
     // TMEM columns
     static constexpr int TM_S = 0;                        // S_t at t * 128 (64 columns)
     static constexpr int TM_P = 64;                       // P(t, b) at t * 128 + 64 + b * 32
-    static constexpr int TM_O = 256;                      // O_t at 256 + t * 128 (D <= 128), single O at D = 256
+    static constexpr int TM_O = SOLO ? 128 : 256;         // O_t at 256 + t * 128 (D <= 128), single O at D = 256; SOLO: 128
     static constexpr int TM_P_LO = 16;                    // hi/lo mode: second P tile 16 columns after the first
     static constexpr int TM_L = 80;                       // MMASUM: L_t at t * 128 + 80 (16 columns, column 0 is read)
     // softmax range management: p' = 2^KOFF * exp2(s - m_used), m_used may lag the true max by <= TAU (log2 units)
@@ -206,7 +219,7 @@ __host__ __device__ constexpr bool pair_uses_poly(int i, int num) {  // spread `
 }
 
 template <class C, bool CAUSAL, bool TOKEN>
-__global__ void __launch_bounds__(C::NTHREADS, 1)
+__global__ void __launch_bounds__(C::NTHREADS, C::CTAS_PER_SM)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, AttnParams p) {
     constexpr int D = C::D;
@@ -235,7 +248,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     QA_STAMP(warp >> 2, 78, 0);
     // ------------------------------------------------------------------ one-time setup
     if (warp == 0) {
-        tmem_alloc(&bars->tmem_base, 512);
+        tmem_alloc(&bars->tmem_base, C::TMEM_COLS);
         tmem_relinquish();
     }
     if (warp == 1) {  // one barrier per lane
@@ -303,13 +316,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (bars->tmem_base != 0) __trap();  // the CTA owns all 512 columns, so the allocation starts at column 0
-    constexpr uint32_t tmem = 0;
+    // PAIR: the CTA owns all 512 columns, so the allocation starts at column 0; SOLO: 0 or 256
+    if (!C::SOLO && bars->tmem_base != 0) __trap();
+    const uint32_t tmem = C::SOLO ? bars->tmem_base : 0u;
 
     // register rebalancing (two-tile configs run 384 threads -> 168 registers each at launch): the softmax
     // warpgroups keep a whole score row per thread in registers, the MMA / TMA warps need almost nothing
     if (warp >= NQ * 4) {
-        if constexpr (NQ == 2) reg_dealloc<56>();
+        if constexpr (C::REBALANCE) reg_dealloc<C::REG_OTHER>();
         if (warp == NQ * 4 + 1) {
             // =========================================================== TMA producer
             if (lane == 0) {
@@ -340,10 +354,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             const uint64_t k_desc0 = make_smem_desc(smem_u32(smem + C::SMEM_K), 16, 8 * C::QK_ROW, qk_swz);
             const uint64_t v_desc0 = make_smem_desc(smem_u32(smem + C::SMEM_V), C::V_BOX_BYTES, 8 * C::V_ROW, v_swz);
             constexpr int KEYS_PER_PV = C::V16 ? 16 : 32;
-            const uint32_t s_t = C::TM_S + t * 128;
-            const uint32_t p_t0 = C::TM_P + t * 128;
-            const uint32_t o_t = C::TM_O + (NQ == 2 ? t * 128 : 0);
-            const uint32_t l_t = C::TM_L + t * 128;
+            const uint32_t s_t = tmem + C::TM_S + t * 128;
+            const uint32_t p_t0 = tmem + C::TM_P + t * 128;
+            const uint32_t o_t = tmem + C::TM_O + (NQ == 2 ? t * 128 : 0);
+            const uint32_t l_t = tmem + C::TM_L + t * 128;
             constexpr uint32_t idesc_l = make_idesc(0, 0, 0, 1, BM, 16);
             const uint64_t ones_desc = make_smem_desc(smem_u32(smem + C::SMEM_ONES), C::V_BOX_BYTES, 8 * C::V_ROW, v_swz);
 
@@ -462,7 +476,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
     } else {
         // =============================================================== softmax / correction / epilogue
-        if constexpr (NQ == 2) reg_alloc<224>();
+        if constexpr (C::REBALANCE) reg_alloc<C::REG_SOFTMAX>();
         const int t = warp >> 2;                       // query tile of this warpgroup
         const int row = ((warp & 3) << 5) | lane;      // row inside the tile == TMEM lane
         const uint32_t lane_base = uint32_t((warp & 3) * 32) << 16;
@@ -807,7 +821,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 512);
+    if (warp == 0) tmem_dealloc(tmem, C::TMEM_COLS);
     QA_STAMP(warp >> 2, 78, 6);
 }
 
@@ -866,6 +880,10 @@ static int launch_cfg(const AttnArgs& a, cudaStream_t stream, int* launches) {
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_TOTAL);
         if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(max dynamic smem)", e);
+        if (C::CTAS_PER_SM > 1) {  // two CTAs per SM need the largest shared-memory carve-out
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(carve-out)", e);
+        }
         attr_done = true;
     }
     dim3 grid((a.Sq + BM * C::NQ - 1) / (BM * C::NQ), a.Hq, a.B);
