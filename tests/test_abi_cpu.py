@@ -54,7 +54,10 @@ def test_argument_validation_without_gpu():
 
     if not torch.cuda.is_available():
         # valid arguments but no device: must fail loudly, never fall back
-        rc = lib.qa_fp8_attn_fwd(16, 16, 16, 2, 16, 16, 16, 0, 16, 0, None, 1, 2, 2, 8, 8, 64, 0, 0.125, 0, None)
+        # (fake pointers: 16-byte aligned inputs, a 32-byte aligned output as the header asks)
+        rc = lib.qa_fp8_attn_fwd(16, 16, 16, 2, 16, 16, 16, 0, 32, 0, None, 1, 2, 2, 8, 8, 64, 0, 0.125, 0, None)
         assert rc in (-2, -3)
-        rc = lib.qa_attn_fwd(16, 16, 16, 0, 16, None, 1, 2, 2, 8, 8, 64, 0, 0.125, None)
+        rc = lib.qa_attn_fwd(16, 16, 16, 0, 32, None, 1, 2, 2, 8, 8, 64, 0, 0.125, None)
         assert rc in (-2, -3)
+    rc = lib.qa_fp8_attn_fwd(16, 16, 16, 2, 16, 16, 16, 0, 16, 0, None, 1, 2, 2, 8, 8, 64, 0, 0.125, 0, None)
+    assert rc == -1 and b"32-byte aligned" in lib.qa_last_error()
