@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define QA_ABI_VERSION 3
+#define QA_ABI_VERSION 4
 
 /* element types */
 #define QA_DT_BF16 0
@@ -41,6 +41,13 @@ extern "C" {
 #define QA_SCALE_HEAD_GIVEN 4     /* qa_quantize_fp8 only: scale[] is an INPUT; quantise with it.  The pair lets a caller
                                     that shards one sequence over several GPUs take the MAX of the per-shard scales
                                     (scale is monotone in amax) and obtain the bytes the unsharded call would produce */
+
+#define QA_WS_PERSISTENT 0x100    /* qa_quantize_fp8, OR-ed into scale_mode: amax_ws was zero-filled ONCE by the caller
+                                    when it was allocated and has since been written only by this library (calls of any
+                                    shape it is large enough for, all ordered on one stream).  The single-pass head-wise
+                                    kernel then skips its per-call clear: its rendezvous slots carry a per-call
+                                    generation tag, and older tags never match.  Without the flag the workspace is plain
+                                    scratch whose contents are ignored (it is cleared by every call). */
 
 /* how P = softmax(QK^T) is fed to the second GEMM */
 #define QA_P_E4M3 0      /* P -> e4m3, V e4m3, tcgen05 kind::f8f6f4               (north-star fast path)          */
@@ -73,7 +80,8 @@ int qa_device_supported(int dev);
  *   x8[i]       out: dense e4m3 bytes [B, H, S[i], D]
  *   scale[i]    out: fp32 [B*H] (QA_SCALE_HEAD) or [B*H*S[i]] (QA_SCALE_TOKEN)
  *   amax_ws     scratch of qa_quantize_workspace_floats(B, H, max_i S[i], D) floats, 8-byte aligned (head-wise only;
- *               may be NULL for token mode); need not be zeroed, must not be shared by calls that can run concurrently
+ *               may be NULL for token mode); need not be zeroed (but see QA_WS_PERSISTENT), must not be shared by
+ *               calls that can run concurrently
  */
 size_t qa_quantize_workspace_floats(int B, int H, int max_S, int D);
 int qa_quantize_fp8(int n_tensors, const void* const* x, int x_dtype, const int64_t* x_strides, void* const* x8,

@@ -15,8 +15,9 @@ from . import build as _build
 
 QA_DT_BF16, QA_DT_FP16, QA_DT_E4M3 = 0, 1, 2
 QA_SCALE_HEAD, QA_SCALE_TOKEN, QA_SCALE_HEAD_TWO_PASS, QA_SCALE_HEAD_AMAX_ONLY, QA_SCALE_HEAD_GIVEN = 0, 1, 2, 3, 4
+QA_WS_PERSISTENT = 0x100  # qa_quantize_fp8: the workspace was zeroed once and is reused (include/qattn.h)
 QA_P_E4M3, QA_P_E4M3_HILO, QA_P_16BIT = 0, 1, 2
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 EXPORTED_SYMBOLS = (
     "qa_abi_version",
@@ -116,11 +117,30 @@ def last_launch_count() -> int:
     return int(load().qa_last_launch_count())
 
 
+_ws_cache = {}  # (device index, stream handle) -> fp32 workspace, zero-filled when allocated, reused by every call
+
+
+def _persistent_workspace(dev: torch.device, n_floats: int) -> torch.Tensor:
+    """The quantiser's workspace under the QA_WS_PERSISTENT contract of include/qattn.h: zeroed once, then only ever
+    written by the library, one per (device, stream) so that the calls sharing it are stream-ordered.  Saves the
+    per-call clear (a memset node and a dependency edge in front of every head-wise quantisation)."""
+    with torch.cuda.device(dev):
+        key = (torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream)
+        ws = _ws_cache.get(key)
+        if ws is None or ws.numel() < n_floats:
+            ws = torch.zeros((max(n_floats, 1 << 16),), dtype=torch.float32, device=dev)
+            _ws_cache[key] = ws
+    return ws
+
+
 def quantize_fp8(tensors: Sequence[torch.Tensor], scale_mode: int,
-                 scales: Optional[Sequence[torch.Tensor]] = None) -> Tuple[list, list]:
+                 scales: Optional[Sequence[torch.Tensor]] = None,
+                 workspace: Optional[torch.Tensor] = None) -> Tuple[list, list]:
     """Quantise 1-3 CUDA tensors [B,H,S_i,D] (bf16/fp16, same B,H,D,dtype) in one launch pair.
 
     Returns ([e4m3 tensors], [fp32 scales: [B,H] head-wise or [B,H,S_i] token-wise]).
+    ``workspace``: optional caller-owned scratch (plain contract: contents ignored); by default a per-(device, stream)
+    workspace under the QA_WS_PERSISTENT contract is used, which saves the per-call clear.
     ``QA_SCALE_HEAD_AMAX_ONLY`` returns ([], scales) without quantising; ``QA_SCALE_HEAD_GIVEN`` quantises with the
     fp32 [B,H] ``scales`` passed in.
     """
@@ -146,7 +166,15 @@ def quantize_fp8(tensors: Sequence[torch.Tensor], scale_mode: int,
     elif scale_mode in (QA_SCALE_HEAD, QA_SCALE_HEAD_TWO_PASS, QA_SCALE_HEAD_AMAX_ONLY):
         scales = [torch.empty((B, H), dtype=torch.float32, device=dev) for _ in xs]
         n_ws = int(lib.qa_quantize_workspace_floats(B, H, max(t.shape[2] for t in xs), D))
-        ws = torch.empty((n_ws,), dtype=torch.float32, device=dev)
+        if workspace is not None:  # caller's scratch, contents ignored (cleared by the call)
+            if workspace.dtype != torch.float32 or workspace.numel() < n_ws or workspace.device != dev:
+                raise ValueError(f"quantize_fp8: workspace must be >= {n_ws} fp32 elements on {dev}")
+            ws = workspace
+        elif os.environ.get("QA_NO_PERSISTENT_WS"):  # developer A/B switch: per-call scratch, cleared by the library
+            ws = torch.empty((n_ws,), dtype=torch.float32, device=dev)
+        else:
+            ws = _persistent_workspace(dev, n_ws)
+            scale_mode |= QA_WS_PERSISTENT
         ws_ptr = ws.data_ptr()
     else:
         scales = [torch.empty((B, H, t.shape[2]), dtype=torch.float32, device=dev) for t in xs]

@@ -75,6 +75,8 @@ int qa_quantize_fp8(int n_tensors, const void* const* x, int x_dtype, const int6
     if (!x || !x_strides || !x8 || !scale || !S) return set_error(QA_ERR_INVALID, "null argument array");
     if (x_dtype != QA_DT_BF16 && x_dtype != QA_DT_FP16)
         return set_error(QA_ERR_INVALID, "x_dtype must be bf16 or fp16");
+    const bool ws_persistent = (scale_mode & QA_WS_PERSISTENT) != 0;
+    scale_mode &= ~QA_WS_PERSISTENT;
     const bool two_pass = scale_mode == QA_SCALE_HEAD_TWO_PASS;
     const bool given = scale_mode == QA_SCALE_HEAD_GIVEN, amax_only = scale_mode == QA_SCALE_HEAD_AMAX_ONLY;
     if (two_pass || given || amax_only) scale_mode = QA_SCALE_HEAD;
@@ -105,6 +107,7 @@ int qa_quantize_fp8(int n_tensors, const void* const* x, int x_dtype, const int6
     a.force_two_pass = two_pass ? 1 : 0;
     a.given_scale = given ? 1 : 0;
     a.amax_only = amax_only ? 1 : 0;
+    a.ws_persistent = ws_persistent ? 1 : 0;
     int max_S = 0;
     for (int i = 0; i < n_tensors; ++i) max_S = S[i] > max_S ? S[i] : max_S;
     a.ws_floats = qa_quantize_workspace_floats(B, H, max_S, D);

@@ -19,6 +19,7 @@ struct QuantArgs {
     int given_scale;  // QA_SCALE_HEAD_GIVEN: scale[] is an input
     int amax_only;    // QA_SCALE_HEAD_AMAX_ONLY: write scale[] only
     size_t ws_floats;
+    int ws_persistent;  // QA_WS_PERSISTENT: no per-call clear of the single-pass kernel's slots
 };
 
 struct AttnArgs {

@@ -1,0 +1,20 @@
+"""Developer tool: a few small, ragged calls of every kernel family - meant to run under compute-sanitizer."""
+import math, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import oracle, quantum_attn
+from quantumattention_b200 import _native
+for (B, H, S, D, causal) in [(1, 2, 333, 128, False), (1, 2, 200, 64, True), (1, 1, 130, 256, True)]:
+    q, k, v = oracle.make_qkv(B, H, S, S, D, seed=1)
+    qc, kc, vc = q.cuda(), k.cuda(), v.cuda()
+    for pv in ("fp8", "fp8_hilo", "16bit"):
+        with quantum_attn.config.patch({"attention.pv_mode": pv}):
+            o = quantum_attn.fp8_attn_func(qc, kc, vc, is_causal=causal)
+    o = quantum_attn.fp8_token_wise_attn_func(qc, kc, vc, is_causal=causal)
+    o = quantum_attn.attn_func(qc, kc, vc, is_causal=causal)
+    (q8, k8, v8), (sq, sk, sv) = _native.quantize_fp8([qc, kc, vc], _native.QA_SCALE_HEAD_TWO_PASS)
+    o, lse = _native.fp8_attn_fwd(q8, k8, v8, sq, sk, sv, scale_mode=0, is_causal=causal, sm_scale=1 / math.sqrt(D),
+                                  p_mode=0, out_dtype=torch.bfloat16, return_lse=True)
+    torch.cuda.synchronize()
+    assert torch.isfinite(o.float()).all() and torch.isfinite(lse).all()
+print("sanitize_small ok")

@@ -169,3 +169,25 @@ def test_quotient_is_correctly_rounded_for_adversarial_scales():
         x = torch.cat([x, -x]).reshape(1, 1, -1, 64).to(torch.bfloat16)
         _check(x, "head-wise")
         _check(x, "token-wise")
+
+
+def test_persistent_workspace_across_shapes_and_paths():
+    """QA_WS_PERSISTENT (include/qattn.h): one zeroed-once workspace serves calls of different shapes through the
+    single-pass and the two-pass kernels in any order - slots are matched by generation tag, never by stale bytes."""
+    shapes = [(1, 6, 4608, 128), (2, 8, 512, 64), (1, 2, 1000, 256), (1, 24, 300, 128), (2, 8, 512, 64), (1, 3, 999, 128)]
+    for i, shape in enumerate(shapes * 2):
+        g = torch.Generator().manual_seed(100 + i)
+        x = torch.randn(shape, generator=g).to(torch.bfloat16)
+        _check(x, "head-wise-2pass" if i % 3 == 1 else "head-wise")
+
+
+def test_plain_scratch_workspace_full_of_garbage():
+    """Without the flag the workspace is plain scratch: whatever it holds (here words that look like valid tags) is
+    cleared by the call."""
+    x = torch.randn((1, 4, 2048, 128), generator=torch.Generator().manual_seed(3)).to(torch.bfloat16)
+    n = int(_native.load().qa_quantize_workspace_floats(1, 4, 2048, 128))
+    for fill in (-1, 1, 2, 3, 7, 1000):
+        ws = torch.full((n,), fill, dtype=torch.int32, device="cuda").view(torch.float32)
+        (x8,), (scale,) = _native.quantize_fp8([x.cuda()], _native.QA_SCALE_HEAD, workspace=ws)
+        b, s = oracle.quantize_fp8(x.float().numpy(), "head-wise")
+        assert np.array_equal(x8.view(torch.uint8).cpu().numpy(), b) and np.array_equal(scale.cpu().numpy(), s)
