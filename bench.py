@@ -186,6 +186,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2_flux", choices=sorted(WORKLOADS))
+    ap.add_argument("--event-every", type=int, default=8,
+                    help="bracket the attention kernel with CUDA events on every N-th timed step (the two event records "
+                         "cost about 6 us of GPU time per bracketed step on C2; 1 = every step)")
     ap.add_argument("--pv-mode", default=None, choices=["fp8", "fp8_hilo", "16bit"])
     ap.add_argument("--e2e-steps", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -262,6 +265,8 @@ def main():
             q, k, v = oracle.make_qkv(B, H, S, S, D, seed=1000 * rank + i)
         sets.append((q.to(dev), k.to(dev), v.to(dev)))
     config["l2_policy"] = f"rotating {n_sets} input sets ({n_sets * bytes_per_set / 1e6:.0f} MB > 126 MB L2)"
+    config["kernel_timing"] = (f"CUDA events around the attention launch of every {args.event_every}-th timed step, on its "
+                               "stream (roofline.achieved is their mean)")
     config["pv_mode"] = pv_mode
 
     from quantumattention_b200 import parallel
@@ -290,8 +295,12 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
+    ev_list = _native.attn_events
     for i in range(args.steps):
+        # the attention launch of every `--event-every`-th step is bracketed by CUDA events (roofline.achieved)
+        _native.attn_events = ev_list if i % args.event_every == 0 else None
         step(i)
+    _native.attn_events = ev_list
     e1.record()
     barrier()
     total_ms = e0.elapsed_time(e1)
