@@ -246,7 +246,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int n_kv = (n_max + 1) >> 1;  // K/V tiles of 128 keys
 
     QA_STAMP(warp >> 2, 78, 0);
+    // the next kernel of the stream (typically the quantiser of the next call) may be scheduled as SMs drain
+    griddep_launch_dependents();
     // ------------------------------------------------------------------ one-time setup
+    // (everything up to the griddep_wait()s below touches no global data: it overlaps the tail of the previous kernel,
+    // normally the quantiser that produces q8 / k8 / v8 and their scales)
     if (warp == 0) {
         tmem_alloc(&bars->tmem_base, C::TMEM_COLS);
         tmem_relinquish();
@@ -294,6 +298,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             tma_prefetch_desc(&tmK);
             tma_prefetch_desc(&tmV);
             tma_prefetch_desc(&tmO);
+            griddep_wait();
             for (int t = 0; t < NQ; ++t) {
                 mbar_arrive_expect_tx(&bars->q_full[t], C::Q_TILE);
                 for (int x = 0; x < C::QK_BOXES; ++x)
@@ -313,6 +318,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             reinterpret_cast<uint32_t*>(smem + C::SMEM_ONES)[i] = 0x38383838u;  // e4m3 1.0
         fence_proxy_async_smem();  // the tensor core reads shared memory through the async proxy
     }
+    griddep_wait();  // (the TMA lane has passed its own wait already: a second one returns at once)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -887,8 +893,8 @@ static int launch_cfg(const AttnArgs& a, cudaStream_t stream, int* launches) {
         attr_done = true;
     }
     dim3 grid((a.Sq + BM * C::NQ - 1) / (BM * C::NQ), a.Hq, a.B);
-    kern<<<grid, C::NTHREADS, C::SMEM_TOTAL, stream>>>(tmQ, tmK, tmV, tmO, p);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = launch_pdl(kern, grid, dim3(C::NTHREADS), size_t(C::SMEM_TOTAL), stream, tmQ, tmK, tmV, tmO, p);
+    if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return set_cuda_error("attn_fwd_kernel launch", e);
     *launches += 1;
     return QA_OK;

@@ -317,6 +317,14 @@ __device__ __forceinline__ void tmem_st_u8(uint32_t taddr, const uint32_t* r) {
                  : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                  : "memory");
 }
+// Programmatic dependent launch.  `griddep_launch_dependents`: the next kernel in the stream (if it was launched with the
+// programmatic-serialisation attribute) may start once every CTA of this grid has said so or exited.  `griddep_wait`:
+// blocks until the previous kernel in the stream has completed and its memory operations are visible - everything a
+// kernel does before it must not touch data the previous kernel produces or still reads.  Both are no-ops for
+// ordinary launches.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // one full 32-byte sector from registers (sm_100: 256-bit global stores)
 __device__ __forceinline__ void st_global_32B(void* ptr, const uint32_t* w) {
     asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(w[0]), "r"(w[1]), "r"(w[2]),

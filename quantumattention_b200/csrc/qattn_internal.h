@@ -4,7 +4,36 @@
 #include <cuda_runtime.h>
 #include "../../include/qattn.h"
 
+#include <cstdlib>
+
 namespace qa {
+
+// Launch with programmatic stream serialisation (programmatic dependent launch): the kernel may be scheduled while the
+// previous kernel of the stream is still draining, and synchronises with it through griddepcontrol.wait (ptx.cuh).
+// QA_PDL=0 in the environment falls back to ordinary launches (developer switch for A/B runs).
+inline bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = std::getenv("QA_PDL");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 
 struct QuantArgs {
     const void* x[3];
