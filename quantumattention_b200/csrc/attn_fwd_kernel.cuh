@@ -76,6 +76,12 @@ constexpr float kLog2e = 1.4426950408889634f;
 #ifndef QA_SOLO
 #define QA_SOLO 0      // 1: one query tile per CTA and two CTAs per SM for D <= 128 (see AttnCfg::SOLO)
 #endif
+#ifndef QA_H2POLY
+#define QA_H2POLY 0    // 1: polynomial exponentials in packed half precision (measured slower: the extra ALU-pipe work)
+#endif
+#ifndef QA_H2POLY_NUM
+#define QA_H2POLY_NUM 5  // of every 8 pairs of exponentials, how many take the half-precision polynomial (single-e4m3 mode)
+#endif
 #ifndef QA_DECIDEQ
 #define QA_DECIDEQ 1   // quads of exponentials left when the rescale decision for the next step is taken
 #endif
@@ -148,8 +154,12 @@ struct AttnCfg {
     static constexpr float KOFF = V16 ? 0.f : 4.f;
     static constexpr float TAU = V16 ? 8.f : 4.f;
     // exponentials on the FMA pipe: polynomial degree (a single e4m3 P tolerates the quadratic's 1.7e-3)
-    // (with the row-sum FADDs gone the FMA pipe has room for one more polynomial pair in eight - measured on C2)
-    static constexpr int POLY_NUM = QA_POLY_NUM + (MMASUM ? 1 : 0);
+    // Single-e4m3 mode with tensor-core row sums: the softmax threads need p' only as e4m3 bytes, so the polynomial
+    // exponentials can run in packed half precision (exp2_pair_h2).  Same accuracy, but measured SLOWER on C2 (148 us with
+    // the fp32 polynomial on 3/8 of the pairs; 156 / 158 / 168 / 180 us with the half-precision one on 4 / 5 / 6 / 8 of 8):
+    // conversions, clamp and exponent insertion land on the half-rate ALU pipe.  Off by default.
+    static constexpr bool H2POLY = (QA_H2POLY != 0) && MMASUM;
+    static constexpr int POLY_NUM = H2POLY ? QA_H2POLY_NUM : QA_POLY_NUM + (MMASUM ? 1 : 0);
     static constexpr int POLY_DEG = (PMODE_ == QA_P_E4M3) ? 2 : 3;
 };
 
@@ -212,6 +222,25 @@ __device__ __forceinline__ float2 exp2_poly(float2 x) {
     r.x = __int_as_float(__float_as_int(q.x) + (__float_as_int(t.x) << 23));
     r.y = __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23));
     return r;
+}
+
+// 2^x for a pair, entirely in packed half precision (one issue cycle per instruction for two elements, where the packed
+// fp32 forms take two): x is rounded to f16 (|x| < 16 here: an absolute error of 2^-7 at most, 0.5 % in 2^x - far below
+// the e4m3 step the result is rounded to), n = round(x) comes from the 1536-magic of f16 with 15 folded in so that the
+// low five mantissa bits of t are n + 15 = the biased f16 exponent of 2^n, f = x - n, 2^f by the quadratic, and the
+// scale 2^n is built by shifting those five bits into the exponent field.  x <= -15 gives exactly 0; x must stay
+// below 16 (the lazy-rescale rule keeps it below KOFF + TAU = 8).  Returns the f16x2 bits.
+__device__ __forceinline__ uint32_t exp2_pair_h2(float2 x) {
+    __half2 xh = __float22half2_rn(x);
+    xh = __hmax2(xh, __float2half2_rn(-15.f));
+    const __half2 magic = __float2half2_rn(1551.f);
+    const __half2 t = __hadd2(xh, magic);
+    const __half2 f = __hsub2(xh, __hsub2(t, magic));
+    __half2 q = __hfma2(f, __float2half2_rn(0.23842893540859222f), __float2half2_rn(0.7034479975700378f));
+    q = __hfma2(q, f, __float2half2_rn(1.0004431009292603f));
+    const uint32_t e = (*reinterpret_cast<const uint32_t*>(&t) & 0x001F001Fu) << 10;
+    const __half2 r = __hmul2(q, *reinterpret_cast<const __half2*>(&e));
+    return *reinterpret_cast<const uint32_t*>(&r);
 }
 
 __host__ __device__ constexpr bool pair_uses_poly(int i, int num) {  // spread `num` of every 8 pairs evenly
@@ -614,6 +643,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             uint32_t pw[C::V16 ? BS / 2 : BS / 4], pw_lo[C::PMODE == QA_P_E4M3_HILO ? BS / 4 : 1];
             // four columns -> P words (and, unless the tensor core sums the rows of P, the running row sum)
             auto exp_quad = [&](int i) {
+                if constexpr (C::H2POLY) {
+                    // each pair goes to e4m3 either from the half-precision polynomial or from two MUFU.EX2
+                    auto bytes2 = [&](int pr) -> uint16_t {
+                        const float2 x = __ffma2_rn(make_float2(s[2 * pr], s[2 * pr + 1]), c2, neg2);
+                        if (pair_uses_poly(pr, C::POLY_NUM)) return cvt_e4m3x2_from_h2(exp2_pair_h2(x));
+                        return cvt_e4m3x2_u16(ex2_approx(x.x), ex2_approx(x.y));
+                    };
+                    const uint16_t lo = bytes2(2 * i), hi = bytes2(2 * i + 1);
+                    pw[i] = join_u16(lo, hi);
+                    return;
+                }
                 const float2 p01 = exp_pair(2 * i), p23 = exp_pair(2 * i + 1);
                 if constexpr (!C::MMASUM) {
                     la = __fadd2_rn(la, p01);

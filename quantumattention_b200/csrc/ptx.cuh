@@ -387,6 +387,22 @@ __device__ __forceinline__ uint32_t pack_e4m3x4(float a, float b, float c, float
     asm("mov.b32 %0, {%1, %2};" : "=r"(r) : "h"(lo), "h"(hi));
     return r;
 }
+// two halves (an f16x2 word) -> two e4m3 bytes
+__device__ __forceinline__ uint16_t cvt_e4m3x2_from_h2(uint32_t h2) {
+    uint16_t r;
+    asm("cvt.rn.satfinite.e4m3x2.f16x2 %0, %1;" : "=h"(r) : "r"(h2));
+    return r;
+}
+__device__ __forceinline__ uint16_t cvt_e4m3x2_u16(float lo, float hi) {
+    uint16_t r;
+    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ uint32_t join_u16(uint16_t lo, uint16_t hi) {
+    uint32_t r;
+    asm("mov.b32 %0, {%1, %2};" : "=r"(r) : "h"(lo), "h"(hi));
+    return r;
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     uint32_t r;
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
