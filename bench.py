@@ -254,15 +254,18 @@ def main():
     # rotating input sets so the working set (> 126 MB L2) is not L2-resident between steps
     bytes_per_set = 3 * B * H * (S // world if ring else S) * D * 2
     n_sets = max(2, math.ceil(300e6 / bytes_per_set))
-    import oracle
+
+    def make_qkv(seed):  # CPU-generated randn so every run (and the CPU arm) sees the same bits
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        return tuple(torch.randn(B, H, S, D, generator=g, dtype=torch.float32).to(torch.bfloat16) for _ in range(3))
 
     S_loc = S // world if ring else S
     sets = []
     for i in range(n_sets):
         if ring:  # every rank generates the same sequence and keeps its slice
-            q, k, v = (t[:, :, rank * S_loc:(rank + 1) * S_loc].contiguous() for t in oracle.make_qkv(B, H, S, S, D, seed=i))
+            q, k, v = (t[:, :, rank * S_loc:(rank + 1) * S_loc].contiguous() for t in make_qkv(i))
         else:
-            q, k, v = oracle.make_qkv(B, H, S, S, D, seed=1000 * rank + i)
+            q, k, v = make_qkv(1000 * rank + i)
         sets.append((q.to(dev), k.to(dev), v.to(dev)))
     config["l2_policy"] = f"rotating {n_sets} input sets ({n_sets * bytes_per_set / 1e6:.0f} MB > 126 MB L2)"
     config["kernel_timing"] = (f"CUDA events around the attention launch of every {args.event_every}-th timed step, on its "
