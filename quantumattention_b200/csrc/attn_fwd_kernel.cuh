@@ -76,6 +76,18 @@ constexpr float kLog2e = 1.4426950408889634f;
 #ifndef QA_SOLO
 #define QA_SOLO 0      // 1: one query tile per CTA and two CTAs per SM for D <= 128 (see AttnCfg::SOLO)
 #endif
+#ifndef QA_MMASUM_D256
+#define QA_MMASUM_D256 0
+#endif
+#ifndef QA_POLY_MS_D64
+#define QA_POLY_MS_D64 3
+#endif
+#ifndef QA_POLY_MS_D256
+#define QA_POLY_MS_D256 1
+#endif
+#ifndef QA_POLY_D256
+#define QA_POLY_D256 2
+#endif
 #ifndef QA_H2POLY
 #define QA_H2POLY 0    // 1: polynomial exponentials in packed half precision (measured slower: the extra ALU-pipe work)
 #endif
@@ -137,7 +149,7 @@ struct AttnCfg {
     // single-e4m3 P mode: the row sums of P are accumulated by the tensor core, L (+)= P . 1, with a constant tile of
     // e4m3 ones (0x38) as the B operand - every byte the MMA can touch holds the same value, so the tile's layout is
     // immaterial - and a 16-column accumulator per query tile in the TMEM columns the 16-bit P buffers leave unused.
-    static constexpr bool MMASUM = (QA_MMASUM != 0) && (PMODE_ == QA_P_E4M3) && !QK16_;
+    static constexpr bool MMASUM = (QA_MMASUM != 0) && (PMODE_ == QA_P_E4M3) && !QK16_ && (D_ != 256 || QA_MMASUM_D256 != 0);
     static constexpr int ONES_BYTES = MMASUM ? 4096 : 0;  // 32 keys x one swizzle span
     static constexpr int SMEM_ONES = O_OWN ? SMEM_O + NQ * O_TILE : SMEM_V + STAGES * V_TILE;
     static constexpr int SMEM_BAR = SMEM_ONES + ONES_BYTES;
@@ -159,7 +171,12 @@ struct AttnCfg {
     // the fp32 polynomial on 3/8 of the pairs; 156 / 158 / 168 / 180 us with the half-precision one on 4 / 5 / 6 / 8 of 8):
     // conversions, clamp and exponent insertion land on the half-rate ALU pipe.  Off by default.
     static constexpr bool H2POLY = (QA_H2POLY != 0) && MMASUM;
-    static constexpr int POLY_NUM = H2POLY ? QA_H2POLY_NUM : QA_POLY_NUM + (MMASUM ? 1 : 0);
+    // The share of polynomial pairs is a per-head-dimension balance, measured with scripts/time_shape.py: at D = 64 the
+    // MUFU is the contended unit (little tensor work per score), at D = 256 a CTA has one softmax warp per scheduler,
+    // the MUFU is never contended and every polynomial is pure extra issue work.
+    static constexpr int POLY_NUM = H2POLY   ? QA_H2POLY_NUM
+                                    : MMASUM ? (D_ == 64 ? QA_POLY_MS_D64 : (D_ == 128 ? QA_POLY_NUM + 1 : QA_POLY_MS_D256))
+                                             : (D_ == 256 ? QA_POLY_D256 : QA_POLY_NUM);
     static constexpr int POLY_DEG = (PMODE_ == QA_P_E4M3) ? 2 : 3;
 };
 
