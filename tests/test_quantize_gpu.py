@@ -155,7 +155,7 @@ def test_long_head_takes_two_pass_path():
 
 
 def test_quotient_is_correctly_rounded_for_adversarial_scales():
-    """The reciprocal-plus-two-corrections quotient must equal IEEE division: bytes identical to the oracle for scales
+    """The reciprocal-plus-correction quotient must give the bytes of IEEE division: bytes identical to the oracle for scales
     whose mantissa is all ones / just above a power of two (worst cases for reciprocal rounding), and every bf16
     magnitude below amax as the numerator."""
     bits = torch.arange(0, 0x7F80, dtype=torch.int32).to(torch.int16)  # every non-negative finite bf16
@@ -169,6 +169,28 @@ def test_quotient_is_correctly_rounded_for_adversarial_scales():
         x = torch.cat([x, -x]).reshape(1, 1, -1, 64).to(torch.bfloat16)
         _check(x, "head-wise")
         _check(x, "token-wise")
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_every_numerator_under_sampled_amax(dtype):
+    """The quantiser divides by its own scale with a reciprocal and ONE residual correction; that this yields the
+    reference's byte was decided by enumerating all (amax, x) pairs on the CPU (scripts/ubench/div_exhaustive.c).  Here
+    the kernels themselves see every 16-bit magnitude (both signs) under each of 96 sampled amax values per dtype -
+    subnormal, tiny (scale clamped to eps), mid-range and largest-finite included."""
+    top = 0x7F7F if dtype == torch.bfloat16 else 0x7BFF
+    rng = np.random.default_rng(20260 + top)
+    amax_bits = np.unique(np.concatenate([[1, 2, 0x7F, 0x80, 0x81, 0x3F80, 0x3C00, 0x0400, 0x03FF, top - 1, top],
+                                          rng.integers(1, top + 1, size=120)]))[:96]
+    mags = np.arange(0, 0x8000, dtype=np.int64)
+    heads = []
+    for ab in amax_bits:
+        m = np.where(mags <= ab, mags, 0)          # magnitudes order like their bit patterns
+        m[0] = ab
+        heads.append(np.concatenate([m, m | 0x8000]).astype(np.uint16))
+    bits = np.stack(heads).reshape(1, len(heads), 512, 128).view(np.int16)
+    x = torch.from_numpy(bits.copy()).view(dtype)
+    for mode in ("head-wise", "head-wise-2pass", "token-wise"):
+        _check(x, mode)
 
 
 def test_persistent_workspace_across_shapes_and_paths():
