@@ -37,7 +37,7 @@ WORKLOADS = {
     "C1": (2, 8, 512, 64, True),
     "C2_flux": (1, 24, 4608, 128, False),
     "C3_llama": (1, 32, 8192, 128, True),
-    # BASELINE.json configs[3]: Wan-720p token count; one GPU runs it whole, N GPUs run the sequence ring (strong scaling)
+    # BASELINE.json configs[3]: Wan-720p token count; one GPU runs it whole, N GPUs shard the sequence (strong scaling; QA_SEQ_STRATEGY=gather|ring)
     "C4_video": (1, 24, 75600, 128, False),
 }
 METRIC = "fp8_attn_fwd_tflops"
@@ -214,7 +214,13 @@ def main():
             raise SystemExit(f"bench.py: S={S} does not split over {world} ranks")
         config["workload"] = (f"{args.workload}: ONE problem B={B} H={H} S={S} D={D} causal={causal} over {world} GPUs, "
                               f"{S // world} tokens per rank, head-wise FP8 scales (global via all_reduce MAX)")
-        config["parallelism"] = f"sequence ring over {world} GPUs: e4m3 K/V blocks by NCCL send/recv, (O, LSE) merge"
+        from quantumattention_b200.parallel import default_seq_strategy
+        config["parallelism"] = (
+            f"sequence sharding over {world} GPUs: e4m3 K/V blocks by NCCL send/recv ring, (O, LSE) merge per block"
+            if default_seq_strategy() == "ring" else
+            f"sequence sharding over {world} GPUs: one NCCL all-gather of the e4m3 K/V blocks under the local block's "
+            f"attention, one launch over the other ranks' keys, one (O, LSE) merge")
+        config["seq_strategy"] = default_seq_strategy()
 
     # ------------------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":

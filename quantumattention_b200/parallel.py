@@ -20,6 +20,7 @@ sm_100a library and has no fallback.
 from __future__ import annotations
 
 import math
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -94,13 +95,53 @@ def _ring_exchange(send_buf: torch.Tensor, recv_buf: torch.Tensor, group) -> lis
     return dist.batch_isend_irecv(ops_)
 
 
+SEQ_STRATEGIES = ("ring", "gather")
+
+
+def default_seq_strategy() -> str:
+    """``QA_SEQ_STRATEGY`` (ring | gather), else the measured choice."""
+    s = os.environ.get("QA_SEQ_STRATEGY", "gather")
+    if s not in SEQ_STRATEGIES:
+        raise ValueError(f"QA_SEQ_STRATEGY must be one of {SEQ_STRATEGIES} but got {s!r}")
+    return s
+
+
+def _gather_blocks(kv_loc: torch.Tensor, world: int, group):
+    """Start the all-gather of every rank's [2,B,H,S,D] e4m3 K/V block; returns ([world,2,B,H,S,D] bytes, work)."""
+    # (the gloo backend of the CPU tests wants the output as a dim-0 concatenation of the inputs)
+    flat = torch.empty((world * kv_loc.shape[0],) + tuple(kv_loc.shape[1:]), dtype=kv_loc.dtype, device=kv_loc.device)
+    work = dist.all_gather_into_tensor(flat, kv_loc, group=group, async_op=True)
+    return flat.view((world,) + tuple(kv_loc.shape)), work
+
+
+def _concat_other_blocks(kv_all: torch.Tensor, rank: int) -> torch.Tensor:
+    """[world,2,B,H,S,D] gathered bytes -> [2,B,H,(world-1)*S,D]: the keys / values of every OTHER rank laid end to
+    end per head (key order is immaterial to non-causal attention).  Two strided copies of 8-byte words."""
+    world, two, B, H, S, D = kv_all.shape
+    dst = torch.empty((two, B, H, (world - 1) * S, D), dtype=kv_all.dtype, device=kv_all.device)
+    wide = torch.int64 if D % 8 == 0 else kv_all.dtype
+    src6 = kv_all.view(wide).permute(1, 2, 3, 0, 4, 5)  # [2,B,H,world,S,D/8]
+    dst6 = dst.view(wide).view(two, B, H, world - 1, S, -1)
+    if rank > 0:
+        dst6[:, :, :, :rank].copy_(src6[:, :, :, :rank])
+    if rank < world - 1:
+        dst6[:, :, :, rank:].copy_(src6[:, :, :, rank + 1:])
+    return dst
+
+
 def ring_fp8_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: Optional[float] = None,
-                       pv_mode: Optional[str] = None, group=None, backend=None) -> torch.Tensor:
+                       pv_mode: Optional[str] = None, group=None, backend=None,
+                       strategy: Optional[str] = None) -> torch.Tensor:
     """Non-causal FP8 attention over a sequence sharded across the ranks of ``group``.
 
     q, k, v: this rank's [B, H, S_local, D] 16-bit slices (equal S_local on every rank); returns the [B, H, S_local, D]
     output rows of the local queries against the keys/values of ALL ranks.  With world size 1 this is exactly
     ``fp8_attn_func(q, k, v)`` in the chosen P mode.
+
+    ``strategy``: how the other ranks' e4m3 K/V reach this one.  "ring": world - 1 neighbour exchanges, one kernel launch
+    and one merge per block.  "gather": ONE all-gather over NVSwitch (every GPU has full bandwidth to every peer, so
+    nothing is won by forwarding hop by hop) that overlaps the attention of the local block, then ONE launch over all
+    the other ranks' keys and one merge - two launches whatever the world size.  Same quantised bytes either way.
     """
     be = backend if backend is not None else NativeBackend()
     world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -110,6 +151,9 @@ def ring_fp8_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, sca
     p_mode = ops.pv_mode_code(pv_mode)
     if p_mode == _native.QA_P_16BIT:
         raise ValueError("ring_fp8_attention moves e4m3 K/V blocks: pv_mode must be 'fp8' or 'fp8_hilo'")
+    strategy = default_seq_strategy() if strategy is None else strategy
+    if strategy not in SEQ_STRATEGIES:
+        raise ValueError(f"strategy must be one of {SEQ_STRATEGIES} but got {strategy!r}")
     B, H, S, D = q.shape
     sm_scale = (1.0 / math.sqrt(D)) if scale is None else float(scale)
 
@@ -121,12 +165,24 @@ def ring_fp8_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, sca
     # 2. quantise once; K and V share one buffer so a ring step is one send and one receive
     q8, k8, v8 = be.quantize([q, k, v], [sq, sk, sv])
     kv = [torch.stack((k8.view(torch.uint8), v8.view(torch.uint8))), None]  # [2, B, H, S, D] bytes
-    if world > 1:
+    if world > 1 and strategy == "ring":
         kv[1] = torch.empty_like(kv[0])
 
     out = torch.empty_like(q)
     o_acc = torch.empty((B, H, S, D), dtype=torch.float32, device=q.device) if world > 1 else None
     lse_acc = torch.empty((B, H, S), dtype=torch.float32, device=q.device)
+    if strategy == "gather" and world > 1:
+        kv_all, work = _gather_blocks(kv[0], world, group)
+        # the local block needs nothing from the wire: attend it while the gather runs
+        o_new, lse_new = be.attend(q8, k8, v8, sq, sk, sv, sm_scale, p_mode, q.dtype)
+        be.merge(o_acc, lse_acc, o_new, lse_new, True, None)
+        work.wait()
+        rest = _concat_other_blocks(kv_all, rank)
+        del kv_all
+        o_new, lse_new = be.attend(q8, rest[0].view(torch.float8_e4m3fn), rest[1].view(torch.float8_e4m3fn), sq, sk, sv,
+                                   sm_scale, p_mode, q.dtype)
+        be.merge(o_acc, lse_acc, o_new, lse_new, False, out)
+        return out
     cur = 0
     for step in range(world):
         last = step == world - 1

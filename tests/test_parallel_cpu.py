@@ -55,13 +55,20 @@ def _ring_worker(rank, world, port, S_local, tmp):
         sl = slice(rank * S_local, (rank + 1) * S_local)
         be = OracleBackend()
         out = parallel.ring_fp8_attention(q[:, :, sl].contiguous(), k[:, :, sl].contiguous(),
-                                          v[:, :, sl].contiguous(), backend=be)
+                                          v[:, :, sl].contiguous(), backend=be, strategy="ring")
         assert be.calls == ["attend", "merge_first"] + ["attend", "merge"] * (world - 1)
+        # the all-gather layout: two launches whatever the world size, same quantised bytes
+        be2 = OracleBackend()
+        out_g = parallel.ring_fp8_attention(q[:, :, sl].contiguous(), k[:, :, sl].contiguous(),
+                                            v[:, :, sl].contiguous(), backend=be2, strategy="gather")
+        assert be2.calls == ["attend", "merge_first", "attend", "merge"]
+        assert torch.allclose(out_g.float(), out.float(), atol=2e-2, rtol=2e-2)
+        assert parallel.default_seq_strategy() in parallel.SEQ_STRATEGIES
         # head-sharded layout on the same data: rank r computes its heads with a stand-in kernel, gather returns all
         def fake_attn(q_, k_, v_):
             return (q_.float() + k_.float().mean(2, keepdim=True) + v_.float().mean(2, keepdim=True)).to(q_.dtype)
         full = parallel.head_sharded_fp8_attention(q, k, v, gather=(H % world == 0), _attn=fake_attn)
-        torch.save({"out": out, "heads": full}, os.path.join(tmp, f"r{rank}.pt"))
+        torch.save({"out": out, "out_gather": out_g, "heads": full}, os.path.join(tmp, f"r{rank}.pt"))
     finally:
         dist.destroy_process_group()
 
@@ -79,10 +86,11 @@ def test_ring_matches_unsharded_oracle(world, tmp_path):
     k8, sk = oracle.quantize_fp8(k.float().numpy(), "head-wise")
     v8, sv = oracle.quantize_fp8(v.float().numpy(), "head-wise")
     ref = oracle.fp8_attention_ref(q8, k8, v8, sq, sk, scale_v=sv)
-    got = torch.cat([torch.load(os.path.join(tmp_path, f"r{r}.pt"))["out"] for r in range(world)], dim=2)
-    m = oracle.compare(got.float().numpy(), ref.numpy())
-    # bf16 partial results and a bf16 output: two roundings of 2^-9
-    assert m["finite"] and m["cos_sim"] > 0.99999 and m["max_abs_over_row_rms"] < 2e-2, m
+    for key in ("out", "out_gather"):
+        got = torch.cat([torch.load(os.path.join(tmp_path, f"r{r}.pt"))[key] for r in range(world)], dim=2)
+        m = oracle.compare(got.float().numpy(), ref.numpy())
+        # bf16 partial results and a bf16 output: two roundings of 2^-9
+        assert m["finite"] and m["cos_sim"] > 0.99999 and m["max_abs_over_row_rms"] < 2e-2, (key, m)
     if H % world == 0:
         heads = [torch.load(os.path.join(tmp_path, f"r{r}.pt"))["heads"] for r in range(world)]
         want = (q.float() + k.float().mean(2, keepdim=True) + v.float().mean(2, keepdim=True)).to(q.dtype)

@@ -139,12 +139,13 @@ def _nccl_ring_worker(rank, world, port, tmp):
         sl = slice(rank * S_local, (rank + 1) * S_local)
         res = {}
         for pv in ("fp8", "fp8_hilo"):
-            out = parallel.ring_fp8_attention(q[:, :, sl].contiguous().cuda(), k[:, :, sl].contiguous().cuda(),
-                                              v[:, :, sl].contiguous().cuda(), pv_mode=pv)
             with quantum_attn.config.patch({"attention.pv_mode": pv}):
                 whole = quantum_attn.fp8_attn_func(q.cuda(), k.cuda(), v.cuda())[:, :, sl]
-            torch.cuda.synchronize()
-            res[pv] = (out.cpu(), whole.cpu())
+            for strategy in parallel.SEQ_STRATEGIES:  # neighbour ring / one all-gather: same bytes, other key partition
+                out = parallel.ring_fp8_attention(q[:, :, sl].contiguous().cuda(), k[:, :, sl].contiguous().cuda(),
+                                                  v[:, :, sl].contiguous().cuda(), pv_mode=pv, strategy=strategy)
+                torch.cuda.synchronize()
+                res[(pv, strategy)] = (out.cpu(), whole.cpu())
         torch.save(res, os.path.join(tmp, f"r{rank}.pt"))
     finally:
         dist.destroy_process_group()
@@ -162,8 +163,11 @@ def test_nccl_ring_matches_unsharded_kernel(tmp_path):
         # Same quantised Q/K/V bytes on both paths.  P is rounded to e4m3 relative to a running maximum that depends on
         # the key-block partition, so two "fp8" results differ by two independent P roundings; with hi+lo P the
         # difference collapses to the bf16 rounding of the partial results.
-        m = oracle.compare(d["fp8"][0].float().numpy(), d["fp8"][1].float().numpy())
-        assert m["cos_sim"] > 0.999 and m["max_abs_over_row_rms"] < 0.4, m
-        m = oracle.compare(d["fp8_hilo"][0].float().numpy(), d["fp8_hilo"][1].float().numpy())
-        # (the largest difference seen is one bf16 ulp of an output element, 2^-10 here: 0.03-0.04 of the row RMS)
-        assert m["cos_sim"] > 0.99999 and m["max_abs_over_row_rms"] < 0.06, m
+        for strategy in parallel.SEQ_STRATEGIES:
+            a, b = d[("fp8", strategy)]
+            m = oracle.compare(a.float().numpy(), b.float().numpy())
+            assert m["cos_sim"] > 0.999 and m["max_abs_over_row_rms"] < 0.4, (strategy, m)
+            a, b = d[("fp8_hilo", strategy)]
+            m = oracle.compare(a.float().numpy(), b.float().numpy())
+            # (the largest difference seen is one bf16 ulp of an output element, 2^-10 here: 0.03-0.04 of the row RMS)
+            assert m["cos_sim"] > 0.99999 and m["max_abs_over_row_rms"] < 0.06, (strategy, m)
