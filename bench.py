@@ -11,8 +11,8 @@ reference's own benchmark times (tests/test_interface.py:90-139).  FLOPs are the
 
 Multi-GPU (torchrun, one rank per GPU): the path shards by batch x head with no collective, so every rank runs its
 own batch element of the same workload (weak scaling); the time is the max over ranks.  The long-video workload
-(C4_video) instead shards ONE sequence over the ranks and runs the e4m3 K/V ring of quantumattention_b200/parallel.py
-(NCCL send/recv overlapped with the kernel; strong scaling).
+(C4_video) instead shards ONE sequence over the ranks (quantumattention_b200/parallel.py: one NCCL all-gather of the
+e4m3 K/V under the local block's attention, or - QA_SEQ_STRATEGY=ring - neighbour send/recv; strong scaling).
 
 ``--impl reference`` times the reference's op definition (src/quantum_attn/ops.py:64-95: dequantise, aten SDPA) on the
 box's host cores - the reference has no CPU kernel and its only GPU kernel is an sm_90a cubin that cannot load on
