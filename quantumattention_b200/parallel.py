@@ -199,6 +199,10 @@ def ring_fp8_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, sca
     return out
 
 
+# the function predates the all-gather strategy; this is the name that says what it does
+sequence_sharded_fp8_attention = ring_fp8_attention
+
+
 def ring_block_owner(rank: int, step: int, world: int) -> int:
     """Rank whose K/V block ``rank`` holds at ring step ``step`` (blocks travel to rank + 1 each step)."""
     return (rank - step) % world
