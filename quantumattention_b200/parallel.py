@@ -9,9 +9,11 @@ src/quantum_attn/tk/attention.py:417,465); callers such as ParaAttention shard t
 * **sequence ring** for shapes whose single (b, h) problems are too long for one GPU's share of the latency budget
   (BASELINE config 4, S = 75 600): each rank owns S/N tokens of Q, K and V.  Q, K, V are quantised ONCE to e4m3 with
   head scales made global by a single ``all_reduce(MAX)`` (12*B*H bytes) - so the bytes are the ones the unsharded
-  call would produce - and the e4m3 K/V blocks (half the bytes of the 16-bit tensors) travel round the ring with
-  ``batch_isend_irecv`` while the fused kernel attends the local queries to the block already here.  Partial results
-  carry their log-sum-exp and are combined by ``qa_merge_partials``.  Non-causal only (as the BASELINE config).
+  call would produce - and the e4m3 K/V blocks (half the bytes of the 16-bit tensors) reach the other ranks either by
+  ONE all-gather over NVSwitch that runs under the attention of the local block (default; two launches and one merge
+  whatever the world size) or round a neighbour ring with ``batch_isend_irecv`` while the fused kernel attends the
+  block already here.  Partial results carry their log-sum-exp and are combined by ``qa_merge_partials``.
+  Non-causal only (as the BASELINE config).
 
 The kernels are reached through a small backend object so that the host logic (ring order, buffer rotation, scale
 exchange, merge order) can be exercised on CPU with the ``gloo`` backend in tests; the default backend is the

@@ -122,3 +122,21 @@ def test_merge_ref_is_exact_split_softmax():
     # an empty side (LSE = -inf) contributes nothing
     o2, l2 = oracle.merge_ref(oa, la, torch.zeros_like(ob), torch.full_like(lb, float("-inf")))
     assert torch.equal(o2, oa) and torch.equal(l2, la)
+
+
+@pytest.mark.parametrize("world,rank", [(2, 0), (2, 1), (4, 2), (8, 0), (8, 7)])
+def test_concat_other_blocks_layout(world, rank):
+    """[world,2,B,H,S,D] gathered bytes -> per head, the blocks of every other rank end to end in rank order."""
+    B, H, S, D = 1, 3, 5, 64
+    g = torch.Generator().manual_seed(world * 10 + rank)
+    kv_all = torch.randint(0, 256, (world, 2, B, H, S, D), dtype=torch.uint8, generator=g)
+    got = parallel._concat_other_blocks(kv_all, rank)
+    want = torch.cat([kv_all[r] for r in range(world) if r != rank], dim=3)
+    assert got.shape == (2, B, H, (world - 1) * S, D) and torch.equal(got, want)
+
+
+def test_unknown_sequence_strategy_is_rejected(monkeypatch):
+    monkeypatch.setenv("QA_SEQ_STRATEGY", "tree")
+    with pytest.raises(ValueError, match="QA_SEQ_STRATEGY"):
+        parallel.default_seq_strategy()
+
