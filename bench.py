@@ -178,6 +178,36 @@ def _claim_stdout():
     return real
 
 
+def accuracy_vs_sdpa(q, k, v, causal, out, heads=(0, -1), v_16bit=False):
+    """BASELINE.json's "cos-sim vs ref": the output of the measured call against plain fp64 softmax(Q K^T) V (torch, on
+    the GPU, outside every timed region) on the DEQUANTISED e4m3 inputs - the reference's op definition
+    (src/quantum_attn/ops.py:64-95) carried to the FP8-V modes - for two heads of the workload.  north_star tolerance:
+    cosine similarity >= 0.999, max-abs error <= 2e-2 of the output RMS (the latter is a bound for the hi+lo / 16-bit
+    P modes; a single e4m3 P carries 2^-4 relative steps per probability)."""
+    from quantumattention_b200 import _native
+
+    (q8, k8, v8), (sq, sk, sv) = _native.quantize_fp8([q, k, v], _native.QA_SCALE_HEAD)
+    D = q.shape[-1]
+    cos, mx = [], []
+    for h in heads:
+        qd = q8[0, h].double() * sq[0, h].double()
+        kd = k8[0, h].double() * sk[0, h].double()
+        # (the 16-bit P/V mode is the reference's own op: V stays in its 16-bit dtype, only Q and K are dequantised)
+        vd = v[0, h].double() if v_16bit else v8[0, h].double() * sv[0, h].double()
+        sc = (qd @ kd.T) / math.sqrt(D)
+        if causal:
+            sc.masked_fill_(torch.ones_like(sc, dtype=torch.bool).triu_(1), float("-inf"))
+        ref = torch.softmax(sc, dim=-1) @ vd
+        got = out[0, h].double()
+        cos.append(float((got * ref).sum() / (got.norm() * ref.norm())))
+        # per-row RMS (tests/: oracle.compare's max_abs_over_row_rms): causal rows near the top are O(1), late rows small
+        mx.append(float(((got - ref).abs() / ref.pow(2).mean(dim=-1, keepdim=True).sqrt()).max()))
+        del sc
+    return {"cos_sim": min(cos), "max_abs_over_row_rms": max(mx), "heads_checked": len(heads),
+            "against": "fp64 softmax(QK^T)V on the dequantised e4m3 Q, K and " + ("16-bit V" if v_16bit else "e4m3 V") +
+                       " (torch on the GPU, untimed)"}
+
+
 def main():
     out = _claim_stdout()
     ap = argparse.ArgumentParser()
@@ -431,6 +461,18 @@ def main():
         ev, _native.attn_events = _native.attn_events, None
         other_modes["attn_func_bf16"] = fl / (statistics.mean(a.elapsed_time(b) for a, b in ev) * 1e-3) / 1e12
 
+    accuracy = None
+    if rank == 0 and not ring:
+        try:
+            accuracy = accuracy_vs_sdpa(*sets[0], causal, attn_call(*sets[0]), v_16bit=(pv_mode == "16bit"))
+            accuracy["pv_mode"] = pv_mode
+            if pv_mode != "fp8_hilo":  # the mode that is built to meet the 2e-2 max-abs bound, for comparison
+                with quantum_attn.config.patch({"attention.pv_mode": "fp8_hilo"}):
+                    hl = accuracy_vs_sdpa(*sets[0], causal, attn_call(*sets[0]))
+                accuracy["fp8_hilo"] = {k_: hl[k_] for k_ in ("cos_sim", "max_abs_over_row_rms")}
+        except Exception as e:  # a reporting extra: never lose the bench line to it
+            accuracy = {"error": repr(e)[:200]}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -486,6 +528,7 @@ def main():
         "per_gpu_tflops": value / world,
         "frac_of_fp8_spec": value / world / FP8_SPEC_TFLOPS,
         "other_pv_modes_kernel_tflops": other_modes,
+        "accuracy": accuracy,
     }
     if world == 1 and not args.no_cpu_baseline:
         leg = cpu_reference_leg(args.workload)
