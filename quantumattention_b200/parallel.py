@@ -100,6 +100,15 @@ def _ring_exchange(send_buf: torch.Tensor, recv_buf: torch.Tensor, group) -> lis
 SEQ_STRATEGIES = ("ring", "gather")
 
 
+def seq_pv_mode() -> str:
+    """P mode of the sequence-sharded path when the caller names none: the configured one, except that the library
+    default "16bit" (V stays 16-bit) cannot apply - e4m3 K/V on the wire is the point of this path - and maps to
+    "fp8"; ask for "fp8_hilo" to stay inside the 2e-2 max-abs bound."""
+    from . import config
+
+    return "fp8" if config.attention.pv_mode == "16bit" else config.attention.pv_mode
+
+
 def default_seq_strategy() -> str:
     """``QA_SEQ_STRATEGY`` (ring | gather), else the measured choice."""
     s = os.environ.get("QA_SEQ_STRATEGY", "gather")
@@ -138,7 +147,7 @@ def ring_fp8_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, sca
 
     q, k, v: this rank's [B, H, S_local, D] 16-bit slices (equal S_local on every rank); returns the [B, H, S_local, D]
     output rows of the local queries against the keys/values of ALL ranks.  With world size 1 this is exactly
-    ``fp8_attn_func(q, k, v)`` in the chosen P mode.
+    ``fp8_attn_func(q, k, v)`` in the chosen P mode (``seq_pv_mode()`` when none is given).
 
     ``strategy``: how the other ranks' e4m3 K/V reach this one.  "ring": world - 1 neighbour exchanges, one kernel launch
     and one merge per block.  "gather": ONE all-gather over NVSwitch (every GPU has full bandwidth to every peer, so
@@ -150,6 +159,8 @@ def ring_fp8_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, sca
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     if q.dim() != 4 or k.shape != v.shape or q.shape[:2] != k.shape[:2] or q.shape[3] != k.shape[3]:
         raise ValueError("ring_fp8_attention: q, k, v must be [B,H,S_local,D] with equal B, H, D (no GQA)")
+    if pv_mode is None:
+        pv_mode = seq_pv_mode()
     p_mode = ops.pv_mode_code(pv_mode)
     if p_mode == _native.QA_P_16BIT:
         raise ValueError("ring_fp8_attention moves e4m3 K/V blocks: pv_mode must be 'fp8' or 'fp8_hilo'")

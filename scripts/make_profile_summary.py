@@ -60,7 +60,9 @@ tj = os.path.join(P, "roofline_traffic.json")
 cur = json.load(open(tj)) if os.path.exists(tj) else {}
 for k, v in traffic.items():
     if "attn_fwd" in k:
-        cur.setdefault("C2_flux", {})["fp8"] = v
+        # AttnCfg<D, PMODE, ...>: the P mode is the kernel's second template argument (0 fp8, 1 fp8_hilo, 2 16bit)
+        pm = {"0": "fp8", "1": "fp8_hilo", "2": "16bit"}.get(os.environ.get("QA_SUMMARY_PMODE", "0"), "fp8")
+        cur.setdefault("C2_flux", {})[pm] = v
     else:
         cur.setdefault("quantiser", {})[k] = v
 cur["_note"] = "dram__bytes_read.sum + dram__bytes_write.sum per launch, from the --set full captures summarised beside this file"

@@ -112,10 +112,12 @@ def test_key_blocks_plus_merge_equal_one_launch(pv):
 
 def test_ring_single_rank_is_fp8_attn_func():
     q, k, v = (t.cuda() for t in oracle.make_qkv(1, 4, 640, 640, 128, seed=4))
-    a = parallel.ring_fp8_attention(q, k, v)
-    b = quantum_attn.fp8_attn_func(q, k, v)
+    a = parallel.ring_fp8_attention(q, k, v)  # no mode named: the configured one, "fp8" when that is "16bit"
+    with quantum_attn.config.patch({"attention.pv_mode": parallel.seq_pv_mode()}):
+        b = quantum_attn.fp8_attn_func(q, k, v)
     torch.cuda.synchronize()
     assert torch.equal(a, b)
+    assert parallel.seq_pv_mode() in ("fp8", "fp8_hilo")
     with pytest.raises(ValueError):
         parallel.ring_fp8_attention(q, k, v, pv_mode="16bit")
 
