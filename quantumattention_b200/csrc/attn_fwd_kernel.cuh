@@ -88,6 +88,9 @@ constexpr float kLog2e = 1.4426950408889634f;
 #ifndef QA_POLY_D256
 #define QA_POLY_D256 2
 #endif
+#ifndef QA_POLY_P16
+#define QA_POLY_P16 QA_POLY_NUM  // 16-bit P mode (the default mode), D <= 128; C2 kernel 177.8 / 173.0 / 167.7 / 173.0 / 175.5 us at 0..4
+#endif
 #ifndef QA_H2POLY
 #define QA_H2POLY 0    // 1: polynomial exponentials in packed half precision (measured slower: the extra ALU-pipe work)
 #endif
@@ -176,7 +179,7 @@ struct AttnCfg {
     // the MUFU is never contended and every polynomial is pure extra issue work.
     static constexpr int POLY_NUM = H2POLY   ? QA_H2POLY_NUM
                                     : MMASUM ? (D_ == 64 ? QA_POLY_MS_D64 : (D_ == 128 ? QA_POLY_NUM + 1 : QA_POLY_MS_D256))
-                                             : (D_ == 256 ? QA_POLY_D256 : QA_POLY_NUM);
+                                             : (D_ == 256 ? QA_POLY_D256 : (PMODE_ == QA_P_16BIT ? QA_POLY_P16 : QA_POLY_NUM));
     static constexpr int POLY_DEG = (PMODE_ == QA_P_E4M3) ? 2 : 3;
 };
 
