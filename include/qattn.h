@@ -11,7 +11,8 @@
  *   - plain pointers to DEVICE memory, sizes as int, no torch types; the caller owns every buffer
  *   - every call is asynchronous on the given stream; no host sync, no allocation inside the library
  *   - return value: 0 = ok, negative = error (see QA_ERR_*); text via qa_last_error() (thread-local)
- *   - tensors are [B, H, S, D]; quantised tensors are DENSE ([B,H,S,D] contiguous, 1 byte per element, e4m3fn)
+ *   - tensors are [B, H, S, D] with D contiguous; inputs may carry batch / head / row strides (a [B,S,H,D]-held
+ *     tensor is consumed in place through TMA); tensors the library WRITES are dense ([B,H,S,D] contiguous)
  *   - the library requires an sm_100 device; there is no fallback path
  */
 #ifndef QATTN_H_
@@ -24,7 +25,7 @@
 extern "C" {
 #endif
 
-#define QA_ABI_VERSION 4
+#define QA_ABI_VERSION 5
 
 /* element types */
 #define QA_DT_BF16 0
@@ -46,8 +47,10 @@ extern "C" {
                                     when it was allocated and has since been written only by this library (calls of any
                                     shape it is large enough for, all ordered on one stream).  The single-pass head-wise
                                     kernel then skips its per-call clear: its rendezvous slots carry a per-call
-                                    generation tag, and older tags never match.  Without the flag the workspace is plain
-                                    scratch whose contents are ignored (it is cleared by every call). */
+                                    generation tag, and older tags never match.  The generation is kept in the workspace
+                                    itself (word 0) and advanced by the kernel, so a call captured into a CUDA graph
+                                    takes a fresh tag on every replay.  Without the flag the workspace is plain scratch
+                                    whose contents are ignored (it is cleared by every call). */
 
 /* how P = softmax(QK^T) is fed to the second GEMM */
 #define QA_P_E4M3 0      /* P -> e4m3, V e4m3, tcgen05 kind::f8f6f4               (north-star fast path)          */
@@ -81,7 +84,9 @@ int qa_device_supported(int dev);
  *   scale[i]    out: fp32 [B*H] (QA_SCALE_HEAD) or [B*H*S[i]] (QA_SCALE_TOKEN)
  *   amax_ws     scratch of qa_quantize_workspace_floats(B, H, max_i S[i], D) floats, 8-byte aligned (head-wise only;
  *               may be NULL for token mode); need not be zeroed (but see QA_WS_PERSISTENT), must not be shared by
- *               calls that can run concurrently
+ *               calls that can run concurrently.  The single-pass head-wise kernel (one CTA per SM, CTAs rendezvous
+ *               through this workspace) needs its whole grid resident at once: if another kernel holds the SMs for
+ *               seconds the launch traps (bounded poll) rather than hangs - serialise such calls per device.
  */
 size_t qa_quantize_workspace_floats(int B, int H, int max_S, int D);
 int qa_quantize_fp8(int n_tensors, const void* const* x, int x_dtype, const int64_t* x_strides, void* const* x8,
@@ -94,9 +99,13 @@ int qa_quantize_fp8(int n_tensors, const void* const* x, int x_dtype, const int6
  * `quantum_attn::fp8_attention_forward` (src/quantum_attn/ops.py:64-95):
  *     out = softmax(sm_scale * (q8*scale_q)(k8*scale_k)^T  [+ top-left causal mask]) (v*scale_v)
  *
- *   q8, k8      dense e4m3 [B,Hq,Sq,D], [B,Hkv,Skv,D]
- *   v           QA_P_E4M3 / QA_P_E4M3_HILO: dense e4m3 [B,Hkv,Skv,D] with scale_v[B*Hkv] (head-wise)
- *               QA_P_16BIT: dense bf16/fp16 (v_dtype) [B,Hkv,Skv,D], scale_v may be NULL
+ *   q8, k8      e4m3 [B,Hq,Sq,D], [B,Hkv,Skv,D]
+ *   v           QA_P_E4M3 / QA_P_E4M3_HILO: e4m3 [B,Hkv,Skv,D] with scale_v[B*Hkv] (head-wise)
+ *               QA_P_16BIT: bf16/fp16 (v_dtype) [B,Hkv,Skv,D], scale_v may be NULL
+ *   q_strides, k_strides, v_strides
+ *               3 ELEMENT strides each - (batch, head, row) - or NULL for a dense tensor; D is contiguous; every stride
+ *               a multiple of 16 bytes.  The tensor maps are built from them, so a [B,S,H,D]-held tensor is read in
+ *               place (the reference copies it dense first, src/quantum_attn/tk/attention.py:419-421)
  *   scale_q/k   fp32, layout per scale_mode (token mode: scale_q[B*Hq*Sq], scale_k[B*Hkv*Skv])
  *   out         dense [B,Hq,Sq,D] of out_dtype (QA_DT_BF16 / QA_DT_FP16), 32-byte aligned
  *   lse         optional fp32 [B*Hq*Sq]: natural-log sum-exp of the scaled scores per row (for merging partial
@@ -107,10 +116,28 @@ int qa_quantize_fp8(int n_tensors, const void* const* x, int x_dtype, const int6
  *   sm_scale    softmax scale; pass 1/sqrt(D) for the reference's behaviour (src/quantum_attn/tk/attention.py:208-210)
  *   Hq % Hkv == 0 (GQA: kv head = q head / (Hq/Hkv)); D in {64, 128, 256}; causal mask is top-left aligned.
  */
-int qa_fp8_attn_fwd(const void* q8, const void* k8, const void* v, int v_dtype, const float* scale_q,
-                    const float* scale_k, const float* scale_v, int scale_mode, void* out, int out_dtype, float* lse,
-                    int B, int Hq, int Hkv, int Sq, int Skv, int D, int causal, float sm_scale, int p_mode,
-                    void* stream);
+int qa_fp8_attn_fwd(const void* q8, const void* k8, const void* v, int v_dtype, const int64_t* q_strides,
+                    const int64_t* k_strides, const int64_t* v_strides, const float* scale_q, const float* scale_k,
+                    const float* scale_v, int scale_mode, void* out, int out_dtype, float* lse, int B, int Hq, int Hkv,
+                    int Sq, int Skv, int D, int causal, float sm_scale, int p_mode, void* stream);
+
+/* The whole of `fp8_attn_func` on 16-bit inputs in ONE call: quantise Q and K (and V in the FP8 P modes), then the
+ * fused forward.  Replaces `_fp8_attention_wrapper` + the op call of the reference (src/quantum_attn/nn.py:394-430:
+ * two `_dynamically_quantize_fp8` + `quantum_attn::fp8_attention_forward`) and saves the host a second crossing of
+ * the boundary per attention call.  Same results as qa_quantize_fp8 followed by qa_fp8_attn_fwd.
+ *
+ *   q, k, v     bf16/fp16 (`dtype`) [B,Hq,Sq,D], [B,Hkv,Skv,D], [B,Hkv,Skv,D] with optional strides as above
+ *   q8, k8, v8  scratch for the dense e4m3 tensors (v8 only in the FP8 P modes, else NULL); they hold the quantised
+ *               tensors on return, so a caller may keep k8 / v8 and their scales for later qa_fp8_attn_fwd calls
+ *   scale_q/k/v out: fp32 scales ([B*H] head-wise, [B*H*S] token-wise for q / k; scale_v always [B*Hkv])
+ *   amax_ws     as for qa_quantize_fp8 (sized for max(Hq, Hkv) heads and max(Sq, Skv) rows); ws_flags 0 or QA_WS_PERSISTENT
+ *   out         dense [B,Hq,Sq,D] of `dtype`; lse optional
+ */
+int qa_fp8_attn_func(const void* q, const void* k, const void* v, int dtype, const int64_t* q_strides,
+                     const int64_t* k_strides, const int64_t* v_strides, void* q8, void* k8, void* v8, float* scale_q,
+                     float* scale_k, float* scale_v, float* amax_ws, int ws_flags, void* out, float* lse, int B, int Hq,
+                     int Hkv, int Sq, int Skv, int D, int causal, float sm_scale, int scale_mode, int p_mode,
+                     void* stream);
 
 /* The same fused forward with Q and K left in 16 bits: S = Q K^T as tcgen05 kind::f16, P and V 16-bit, fp32
  * accumulation and softmax.  Replaces the reference's non-FP8 TK module - `attention_forward(q, k, v, causal)`
@@ -119,12 +146,14 @@ int qa_fp8_attn_fwd(const void* q8, const void* k8, const void* v, int v_dtype, 
  * (src/quantum_attn/ops.py:32-45):
  *     out = softmax(sm_scale * q k^T  [+ top-left causal mask]) v
  *
- *   q, k, v     dense [B,Hq,Sq,D], [B,Hkv,Skv,D], [B,Hkv,Skv,D], all of `dtype` (QA_DT_BF16 / QA_DT_FP16)
+ *   q, k, v     [B,Hq,Sq,D], [B,Hkv,Skv,D], [B,Hkv,Skv,D], all of `dtype` (QA_DT_BF16 / QA_DT_FP16), optional element
+ *               strides (batch, head, row) as in qa_fp8_attn_fwd
  *   out         dense [B,Hq,Sq,D] of `dtype`;  lse as in qa_fp8_attn_fwd (NULL to skip)
  *   Hq % Hkv == 0; D in {64, 128, 256}; causal mask is top-left aligned.
  */
-int qa_attn_fwd(const void* q, const void* k, const void* v, int dtype, void* out, float* lse, int B, int Hq, int Hkv,
-                int Sq, int Skv, int D, int causal, float sm_scale, void* stream);
+int qa_attn_fwd(const void* q, const void* k, const void* v, int dtype, const int64_t* q_strides,
+                const int64_t* k_strides, const int64_t* v_strides, void* out, float* lse, int B, int Hq, int Hkv, int Sq,
+                int Skv, int D, int causal, float sm_scale, void* stream);
 
 /* Combine two partial attention results over disjoint key sets, row by row:
  *     m = max(lse_acc, lse_new); w_x = exp(lse_x - m); O = (w_acc O_acc + w_new O_new) / (w_acc + w_new);

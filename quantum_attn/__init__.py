@@ -4,7 +4,7 @@ import sys
 
 import quantumattention_b200 as _impl
 from quantumattention_b200 import *  # noqa: F401,F403
-from quantumattention_b200 import __all__, __version__, config, nn, ops, quantum_attn_interface  # noqa: F401
+from quantumattention_b200 import QuantizedKV, __all__, __version__, config, nn, ops, quantize_kv, quantum_attn_interface  # noqa: F401
 
 for _name in ("config", "nn", "ops", "quantum_attn_interface"):
     sys.modules[f"{__name__}.{_name}"] = getattr(_impl, _name)

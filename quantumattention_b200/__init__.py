@@ -4,6 +4,7 @@ of WaveSpeedAI/QuantumAttention, behind the reference's own Python entry points
 resolves to this package, so reference users switch without touching call sites.
 """
 from . import config, nn, ops, quantum_attn_interface  # noqa: F401
+from .nn import QuantizedKV, quantize_kv  # noqa: F401  (extension: quantise K / V once, attend many times)
 from .quantum_attn_interface import (
     attn_func,
     attn_func_with_fallback,

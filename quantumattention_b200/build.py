@@ -39,18 +39,34 @@ def _stale(target: str, deps) -> bool:
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
+    """Build the library if it is missing or older than its sources.  Safe to call from several processes at once
+    (one rank per GPU on a fresh tree): an inter-process lock lets one of them build, the others wait and re-check,
+    and the library appears under its final name by an atomic rename, never half-written."""
+    import fcntl
+
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
     deps = srcs + [os.path.normpath(os.path.join(CSRC, h)) for h in HEADERS]
-    if force or _stale(LIB_PATH, deps):
-        compile_and_link(LIB_PATH, srcs, extra=["-Xptxas=-v"] if verbose else [], verbose=verbose)
+    if not (force or _stale(LIB_PATH, deps)):
+        return LIB_PATH
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    with open(os.path.join(HERE, "build", ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if force or _stale(LIB_PATH, deps):  # (another process may have built it while this one waited)
+                tmp = LIB_PATH + f".tmp.{os.getpid()}"
+                compile_and_link(tmp, srcs, extra=["-Xptxas=-v"] if verbose else [], verbose=verbose,
+                                 objdir=os.path.join(HERE, "build", os.path.basename(LIB_PATH) + ".d"))
+                os.replace(tmp, LIB_PATH)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 
-def compile_and_link(out: str, srcs, extra=(), verbose: bool = False) -> None:
+def compile_and_link(out: str, srcs, extra=(), verbose: bool = False, objdir: str = None) -> None:
     """One nvcc -c per translation unit, all at once (attn_fwd.cu dominates), then a link step."""
     from concurrent.futures import ThreadPoolExecutor
 
-    objdir = os.path.join(HERE, "build", os.path.basename(out) + ".d")
+    objdir = objdir or os.path.join(HERE, "build", os.path.basename(out) + ".d")
     os.makedirs(objdir, exist_ok=True)
     objs = [os.path.join(objdir, os.path.basename(s) + ".o") for s in srcs]
 

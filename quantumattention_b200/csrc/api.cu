@@ -35,6 +35,22 @@ static int check_device() {
     return QA_OK;
 }
 
+// Element strides (batch, head, row) of a [B, H, S, D] tensor whose last dim is contiguous; NULL = dense.  TMA wants
+// every stride a multiple of 16 bytes; dims of size 1 take the dense value (frameworks report arbitrary ones there).
+static int take_strides(int64_t (&dst)[3], const int64_t* src, int B, int H, int S, int D, int elem_bytes,
+                        const char* name) {
+    const int64_t dense[3] = {int64_t(H) * S * D, int64_t(S) * D, int64_t(D)};
+    const int sizes[3] = {B, H, S};
+    for (int i = 0; i < 3; ++i) {
+        dst[i] = (src && sizes[i] > 1) ? src[i] : dense[i];
+        if (dst[i] <= 0 || (dst[i] * elem_bytes) % 16 != 0)
+            return set_error(QA_ERR_INVALID, "%s: stride %d (%lld elements) must be positive and a multiple of 16 bytes",
+                             name, i, (long long)dst[i]);
+    }
+    if (dst[2] < D) return set_error(QA_ERR_INVALID, "%s: row stride %lld is smaller than the head dimension %d", name, (long long)dst[2], D);
+    return QA_OK;
+}
+
 }  // namespace qa
 
 using namespace qa;
@@ -60,17 +76,17 @@ int qa_device_supported(int dev) {
 }
 
 size_t qa_quantize_workspace_floats(int B, int H, int max_S, int D) {
-    // two-pass kernels: amax cells [3BH] (+ spare);  single-pass kernel: one 8-byte slot per 32 KB slab of 3 tensors
+    // 8 header words (generation, check-in counter);  two-pass kernels: amax cells [3BH] (+ spare);  single-pass
+    // kernel: one 8-byte slot per 32 KB slab of 3 tensors
     if (B < 1 || H < 1 || max_S < 1 || D < 1) return 0;
     const size_t slab_rows = 32768 / (size_t(D) * 2) ? 32768 / (size_t(D) * 2) : 1;
     const size_t slabs = (size_t(max_S) + slab_rows - 1) / slab_rows * 3 * size_t(B) * size_t(H);
-    return size_t(6) * size_t(B) * size_t(H) + 8 + 2 * slabs;
+    return size_t(8) + size_t(6) * size_t(B) * size_t(H) + 8 + 2 * slabs;
 }
 
-int qa_quantize_fp8(int n_tensors, const void* const* x, int x_dtype, const int64_t* x_strides, void* const* x8,
-                    float* const* scale, float* amax_ws, int B, int H, const int* S, int D, int scale_mode,
-                    void* stream) {
-    g_launches = 0;
+static int quantize_call(int n_tensors, const void* const* x, int x_dtype, const int64_t* x_strides, void* const* x8,
+                         float* const* scale, float* amax_ws, int B, int H, const int* S, int D, int scale_mode,
+                         void* stream) {
     if (n_tensors < 1 || n_tensors > 3) return set_error(QA_ERR_INVALID, "n_tensors must be 1..3, got %d", n_tensors);
     if (!x || !x_strides || !x8 || !scale || !S) return set_error(QA_ERR_INVALID, "null argument array");
     if (x_dtype != QA_DT_BF16 && x_dtype != QA_DT_FP16)
@@ -85,6 +101,7 @@ int qa_quantize_fp8(int n_tensors, const void* const* x, int x_dtype, const int6
     if (D != 64 && D != 128 && D != 256) return set_error(QA_ERR_INVALID, "Unsupported head dimension: %d", D);
     if (B < 1 || H < 1 || int64_t(B) * H > 65535) return set_error(QA_ERR_INVALID, "B*H out of range");
     if (scale_mode == QA_SCALE_HEAD && !given && !amax_ws) return set_error(QA_ERR_INVALID, "amax_ws required for head-wise");
+    if (reinterpret_cast<uintptr_t>(amax_ws) & 7) return set_error(QA_ERR_INVALID, "amax_ws must be 8-byte aligned");
     QuantArgs a;
     memset(&a, 0, sizeof(a));
     for (int i = 0; i < n_tensors; ++i) {
@@ -103,7 +120,8 @@ int qa_quantize_fp8(int n_tensors, const void* const* x, int x_dtype, const int6
         a.S[i] = S[i];
     }
     a.B = B, a.H = H, a.D = D;
-    a.amax_ws = amax_ws;
+    a.ctl = reinterpret_cast<unsigned int*>(amax_ws);
+    a.cells = amax_ws ? amax_ws + 8 : nullptr;
     a.force_two_pass = two_pass ? 1 : 0;
     a.given_scale = given ? 1 : 0;
     a.amax_only = amax_only ? 1 : 0;
@@ -116,11 +134,17 @@ int qa_quantize_fp8(int n_tensors, const void* const* x, int x_dtype, const int6
     return quantize_dispatch(a, x_dtype, scale_mode, n_tensors, static_cast<cudaStream_t>(stream), &g_launches);
 }
 
-int qa_fp8_attn_fwd(const void* q8, const void* k8, const void* v, int v_dtype, const float* scale_q,
-                    const float* scale_k, const float* scale_v, int scale_mode, void* out, int out_dtype, float* lse,
-                    int B, int Hq, int Hkv, int Sq, int Skv, int D, int causal, float sm_scale, int p_mode,
+int qa_quantize_fp8(int n_tensors, const void* const* x, int x_dtype, const int64_t* x_strides, void* const* x8,
+                    float* const* scale, float* amax_ws, int B, int H, const int* S, int D, int scale_mode,
                     void* stream) {
     g_launches = 0;
+    return quantize_call(n_tensors, x, x_dtype, x_strides, x8, scale, amax_ws, B, H, S, D, scale_mode, stream);
+}
+
+static int fp8_attn_call(const void* q8, const void* k8, const void* v, int v_dtype, const int64_t* q_strides,
+                         const int64_t* k_strides, const int64_t* v_strides, const float* scale_q, const float* scale_k,
+                         const float* scale_v, int scale_mode, void* out, int out_dtype, float* lse, int B, int Hq,
+                         int Hkv, int Sq, int Skv, int D, int causal, float sm_scale, int p_mode, void* stream) {
     if (!q8 || !k8 || !v || !scale_q || !scale_k || !out) return set_error(QA_ERR_INVALID, "null pointer argument");
     if (D != 64 && D != 128 && D != 256) return set_error(QA_ERR_INVALID, "Unsupported head dimension: %d", D);
     if (B < 1 || Hq < 1 || Hkv < 1 || Sq < 1 || Skv < 1) return set_error(QA_ERR_INVALID, "empty problem");
@@ -145,9 +169,12 @@ int qa_fp8_attn_fwd(const void* q8, const void* k8, const void* v, int v_dtype, 
     if ((reinterpret_cast<uintptr_t>(q8) | reinterpret_cast<uintptr_t>(k8) | reinterpret_cast<uintptr_t>(v)) & 15)
         return set_error(QA_ERR_INVALID, "tensor base pointers must be 16-byte aligned");
     if (reinterpret_cast<uintptr_t>(out) & 31) return set_error(QA_ERR_INVALID, "out must be 32-byte aligned");
-    int rc = check_device();
-    if (rc != QA_OK) return rc;
     AttnArgs a;
+    int rc;
+    if ((rc = take_strides(a.qs, q_strides, B, Hq, Sq, D, 1, "q8")) != QA_OK) return rc;
+    if ((rc = take_strides(a.ks, k_strides, B, Hkv, Skv, D, 1, "k8")) != QA_OK) return rc;
+    if ((rc = take_strides(a.vs, v_strides, B, Hkv, Skv, D, p_mode == QA_P_16BIT ? 2 : 1, "v")) != QA_OK) return rc;
+    if ((rc = check_device()) != QA_OK) return rc;
     a.q8 = q8, a.k8 = k8, a.v = v;
     a.scale_q = scale_q, a.scale_k = scale_k, a.scale_v = scale_v;
     a.out = out, a.lse = lse;
@@ -162,8 +189,77 @@ int qa_fp8_attn_fwd(const void* q8, const void* k8, const void* v, int v_dtype, 
     return attn_fwd_dispatch(a, static_cast<cudaStream_t>(stream), &g_launches);
 }
 
-int qa_attn_fwd(const void* q, const void* k, const void* v, int dtype, void* out, float* lse, int B, int Hq, int Hkv,
-                int Sq, int Skv, int D, int causal, float sm_scale, void* stream) {
+int qa_fp8_attn_fwd(const void* q8, const void* k8, const void* v, int v_dtype, const int64_t* q_strides,
+                    const int64_t* k_strides, const int64_t* v_strides, const float* scale_q, const float* scale_k,
+                    const float* scale_v, int scale_mode, void* out, int out_dtype, float* lse, int B, int Hq, int Hkv,
+                    int Sq, int Skv, int D, int causal, float sm_scale, int p_mode, void* stream) {
+    g_launches = 0;
+    return fp8_attn_call(q8, k8, v, v_dtype, q_strides, k_strides, v_strides, scale_q, scale_k, scale_v, scale_mode, out,
+                         out_dtype, lse, B, Hq, Hkv, Sq, Skv, D, causal, sm_scale, p_mode, stream);
+}
+
+int qa_fp8_attn_func(const void* q, const void* k, const void* v, int dtype, const int64_t* q_strides,
+                     const int64_t* k_strides, const int64_t* v_strides, void* q8, void* k8, void* v8, float* scale_q,
+                     float* scale_k, float* scale_v, float* amax_ws, int ws_flags, void* out, float* lse, int B, int Hq,
+                     int Hkv, int Sq, int Skv, int D, int causal, float sm_scale, int scale_mode, int p_mode,
+                     void* stream) {
+    g_launches = 0;
+    if (!q || !k || !v || !q8 || !k8 || !scale_q || !scale_k || !out) return set_error(QA_ERR_INVALID, "null pointer argument");
+    if (scale_mode != QA_SCALE_HEAD && scale_mode != QA_SCALE_TOKEN)
+        return set_error(QA_ERR_INVALID, "Unsupported scaling_method code: %d", scale_mode);
+    if (ws_flags & ~QA_WS_PERSISTENT) return set_error(QA_ERR_INVALID, "ws_flags may only carry QA_WS_PERSISTENT");
+    const bool v_fp8 = p_mode != QA_P_16BIT;
+    if (v_fp8 && (!v8 || !scale_v)) return set_error(QA_ERR_INVALID, "FP8 P modes need v8 and scale_v buffers");
+    if (B < 1 || Hq < 1 || Hkv < 1) return set_error(QA_ERR_INVALID, "empty problem");
+    // strides as the quantiser wants them: 4 per tensor, the last one 1
+    auto four = [](int64_t (&d)[4], const int64_t* s, int H, int S, int D) {
+        d[0] = s ? s[0] : int64_t(H) * S * D, d[1] = s ? s[1] : int64_t(S) * D, d[2] = s ? s[2] : int64_t(D), d[3] = 1;
+    };
+    int64_t st[3][4];
+    four(st[0], q_strides, Hq, Sq, D);
+    four(st[1], k_strides, Hkv, Skv, D);
+    four(st[2], v_strides, Hkv, Skv, D);
+    int rc;
+    // one quantiser launch for everything that shares a head count (head-wise V rides along with K; token-wise Q / K
+    // scales leave V, whose scale is always per head, to a launch of its own)
+    const bool v_with_k = v_fp8 && scale_mode == QA_SCALE_HEAD;
+    if (Hq == Hkv) {
+        const void* x[3] = {q, k, v};
+        void* x8[3] = {q8, k8, v8};
+        float* sc[3] = {scale_q, scale_k, scale_v};
+        const int S[3] = {Sq, Skv, Skv};
+        rc = quantize_call(v_with_k ? 3 : 2, x, dtype, &st[0][0], x8, sc, amax_ws, B, Hq, S, D, scale_mode | ws_flags, stream);
+        if (rc != QA_OK) return rc;
+    } else {
+        const void* xq[1] = {q};
+        void* xq8[1] = {q8};
+        float* sq[1] = {scale_q};
+        const int Sq1[1] = {Sq};
+        rc = quantize_call(1, xq, dtype, &st[0][0], xq8, sq, amax_ws, B, Hq, Sq1, D, scale_mode | ws_flags, stream);
+        if (rc != QA_OK) return rc;
+        const void* x[2] = {k, v};
+        void* x8[2] = {k8, v8};
+        float* sc[2] = {scale_k, scale_v};
+        const int S[2] = {Skv, Skv};
+        rc = quantize_call(v_with_k ? 2 : 1, x, dtype, &st[1][0], x8, sc, amax_ws, B, Hkv, S, D, scale_mode | ws_flags, stream);
+        if (rc != QA_OK) return rc;
+    }
+    if (v_fp8 && !v_with_k) {
+        const void* x[1] = {v};
+        void* x8[1] = {v8};
+        float* sc[1] = {scale_v};
+        const int S[1] = {Skv};
+        rc = quantize_call(1, x, dtype, &st[2][0], x8, sc, amax_ws, B, Hkv, S, D, QA_SCALE_HEAD | ws_flags, stream);
+        if (rc != QA_OK) return rc;
+    }
+    return fp8_attn_call(q8, k8, v_fp8 ? v8 : v, v_fp8 ? QA_DT_E4M3 : dtype, nullptr, nullptr, v_fp8 ? nullptr : v_strides,
+                         scale_q, scale_k, v_fp8 ? scale_v : nullptr, scale_mode, out, dtype, lse, B, Hq, Hkv, Sq, Skv, D,
+                         causal, sm_scale, p_mode, stream);
+}
+
+int qa_attn_fwd(const void* q, const void* k, const void* v, int dtype, const int64_t* q_strides,
+                const int64_t* k_strides, const int64_t* v_strides, void* out, float* lse, int B, int Hq, int Hkv, int Sq,
+                int Skv, int D, int causal, float sm_scale, void* stream) {
     g_launches = 0;
     if (!q || !k || !v || !out) return set_error(QA_ERR_INVALID, "null pointer argument");
     if (dtype != QA_DT_BF16 && dtype != QA_DT_FP16)
@@ -177,9 +273,12 @@ int qa_attn_fwd(const void* q, const void* k, const void* v, int dtype, void* ou
     if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v)) & 15)
         return set_error(QA_ERR_INVALID, "tensor base pointers must be 16-byte aligned");
     if (reinterpret_cast<uintptr_t>(out) & 31) return set_error(QA_ERR_INVALID, "out must be 32-byte aligned");
-    int rc = check_device();
-    if (rc != QA_OK) return rc;
     AttnArgs a;
+    int rc;
+    if ((rc = take_strides(a.qs, q_strides, B, Hq, Sq, D, 2, "q")) != QA_OK) return rc;
+    if ((rc = take_strides(a.ks, k_strides, B, Hkv, Skv, D, 2, "k")) != QA_OK) return rc;
+    if ((rc = take_strides(a.vs, v_strides, B, Hkv, Skv, D, 2, "v")) != QA_OK) return rc;
+    if ((rc = check_device()) != QA_OK) return rc;
     a.q8 = q, a.k8 = k, a.v = v;
     a.scale_q = a.scale_k = a.scale_v = nullptr;
     a.out = out, a.lse = lse;

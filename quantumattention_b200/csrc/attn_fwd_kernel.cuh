@@ -321,15 +321,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const int s = n % C::STAGES;
         mbar_arrive_expect_tx(&bars->k_full[s], C::K_TILE);
         for (int x = 0; x < C::QK_BOXES; ++x)
-            tma_load_3d(smem + C::SMEM_K + s * C::K_TILE + x * C::QK_BOX_BYTES, &tmK, &bars->k_full[s],
-                        x * (C::QK_ROW / C::QB), n * BN, bhkv, kEvictLast);
+            tma_load_4d(smem + C::SMEM_K + s * C::K_TILE + x * C::QK_BOX_BYTES, &tmK, &bars->k_full[s],
+                        x * (C::QK_ROW / C::QB), n * BN, hkv, b, kEvictLast);
     };
     auto load_v = [&](int n) {
         const int s = n % C::STAGES;
         mbar_arrive_expect_tx(&bars->v_full[s], C::V_TILE);
         for (int x = 0; x < C::V_BOXES; ++x)
-            tma_load_3d(smem + C::SMEM_V + s * C::V_TILE + x * C::V_BOX_BYTES, &tmV, &bars->v_full[s],
-                        x * (C::V_ROW / C::VB), n * BN, bhkv, kEvictLast);
+            tma_load_4d(smem + C::SMEM_V + s * C::V_TILE + x * C::V_BOX_BYTES, &tmV, &bars->v_full[s],
+                        x * (C::V_ROW / C::VB), n * BN, hkv, b, kEvictLast);
     };
     if (warp == NQ * 4 + 1) {
         if (lane < 4) {
@@ -351,8 +351,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             for (int t = 0; t < NQ; ++t) {
                 mbar_arrive_expect_tx(&bars->q_full[t], C::Q_TILE);
                 for (int x = 0; x < C::QK_BOXES; ++x)
-                    tma_load_3d(smem + C::SMEM_Q + t * C::Q_TILE + x * C::QK_BOX_BYTES, &tmQ, &bars->q_full[t],
-                                x * (C::QK_ROW / C::QB), m0 + t * BM, bh, kEvictFirst);
+                    tma_load_4d(smem + C::SMEM_Q + t * C::Q_TILE + x * C::QK_BOX_BYTES, &tmQ, &bars->q_full[t],
+                                x * (C::QK_ROW / C::QB), m0 + t * BM, h, b, kEvictFirst);
                 if (t == 0) load_kv(0);  // K tile 0 right behind the first Q tile: S_0 needs exactly these two
             }
             load_v(0);
@@ -902,18 +902,17 @@ static int launch_cfg(const AttnArgs& a, cudaStream_t stream, int* launches) {
     const CUtensorMapDataType qkdt = !C::QK16 ? CU_TENSOR_MAP_DATA_TYPE_UINT8
                                      : (a.qk_dtype == QA_DT_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
                                                                  : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
-    ok &= make_tmap_3d(&tmQ, qkdt, C::QB, a.q8, D, a.Sq, uint64_t(a.B) * a.Hq, D * C::QB, D * C::QB * a.Sq,
+    // Q, K, V in place through their own batch / head / row strides (element strides in AttnArgs, D contiguous)
+    ok &= make_tmap_4d(&tmQ, qkdt, a.q8, D, a.Sq, a.Hq, a.B, a.qs[2] * C::QB, a.qs[1] * C::QB, a.qs[0] * C::QB,
                        C::QK_ROW / C::QB, BM, qk_swz);
-    ok &= make_tmap_3d(&tmK, qkdt, C::QB, a.k8, D, a.Skv, uint64_t(a.B) * a.Hkv, D * C::QB, D * C::QB * a.Skv,
+    ok &= make_tmap_4d(&tmK, qkdt, a.k8, D, a.Skv, a.Hkv, a.B, a.ks[2] * C::QB, a.ks[1] * C::QB, a.ks[0] * C::QB,
                        C::QK_ROW / C::QB, BN, qk_swz);
-    if (C::V16) {
-        const CUtensorMapDataType dt =
-            a.v_dtype == QA_DT_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-        ok &= make_tmap_3d(&tmV, dt, 2, a.v, D, a.Skv, uint64_t(a.B) * a.Hkv, D * 2, D * 2 * a.Skv, C::V_ROW / 2, BN,
-                           v_swz);
-    } else {
-        ok &= make_tmap_3d(&tmV, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, a.v, D, a.Skv, uint64_t(a.B) * a.Hkv, D, D * a.Skv,
-                           C::V_ROW, BN, v_swz);
+    {
+        const CUtensorMapDataType dt = !C::V16 ? CU_TENSOR_MAP_DATA_TYPE_UINT8
+                                       : (a.v_dtype == QA_DT_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                                                  : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+        ok &= make_tmap_4d(&tmV, dt, a.v, D, a.Skv, a.Hkv, a.B, a.vs[2] * C::VB, a.vs[1] * C::VB, a.vs[0] * C::VB,
+                           C::V_ROW / C::VB, BN, v_swz);
     }
     const CUtensorMapDataType odt =
         a.out_dtype == QA_DT_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
@@ -942,15 +941,16 @@ static int launch_cfg(const AttnArgs& a, cudaStream_t stream, int* launches) {
 #endif
 
     auto kern = attn_fwd_kernel<C, CAUSAL, TOKEN>;
-    static bool attr_done = false;  // per instantiation; racing threads set the same value
-    if (!attr_done) {
+    static DeviceSet attr_done;  // per instantiation and per device (function attributes belong to a device)
+    const int dev = current_device();
+    if (!attr_done.has(dev)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_TOTAL);
         if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(max dynamic smem)", e);
         if (C::CTAS_PER_SM > 1) {  // two CTAs per SM need the largest shared-memory carve-out
             e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(carve-out)", e);
         }
-        attr_done = true;
+        attr_done.add(dev);
     }
     dim3 grid((a.Sq + BM * C::NQ - 1) / (BM * C::NQ), a.Hq, a.B);
     cudaError_t e = launch_pdl(kern, grid, dim3(C::NTHREADS), size_t(C::SMEM_TOTAL), stream, tmQ, tmK, tmV, tmO, p);

@@ -112,13 +112,8 @@ static void launch_merge(const MergeArgs& a, int grid, cudaStream_t stream) {
 }
 
 int merge_dispatch(const MergeArgs& a, cudaStream_t stream, int* launches) {
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-            n = 148;
-        sms = n;
-    }
+    int sms = sm_count();
+    if (sms <= 0) sms = 148;
     const int rows_per_cta = kMergeThreads / (a.D >> 3);
     const long long want = (a.rows + rows_per_cta - 1) / rows_per_cta;
     const long long cap = (long long)sms * 8 * 4;  // 8 resident CTAs per SM, a few trips each

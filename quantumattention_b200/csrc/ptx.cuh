@@ -110,6 +110,16 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
           "r"(c2), "l"(policy)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                            int c2, int c3, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+        :
+        : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
+          "r"(c2), "r"(c3), "l"(policy)
+        : "memory");
+}
 // 1-D bulk copy global -> shared (size and both addresses multiples of 16 bytes), completion on an mbarrier
 __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar,
                                              uint64_t policy) {

@@ -4,9 +4,43 @@
 #include <cuda_runtime.h>
 #include "../../include/qattn.h"
 
+#include <atomic>
 #include <cstdlib>
 
 namespace qa {
+
+// Per-device one-time state.  Function attributes (dynamic shared-memory opt-in, carve-out) and the SM count belong to
+// a device, not to the process: one process may drive several GPUs (SURVEY.md section 8b "threading / streams").
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    return dev;
+}
+// A set of device ordinals ("has X been done on device d"); racing threads set the same bit.
+struct DeviceSet {
+    std::atomic<unsigned long long> bits{0};
+    bool has(int dev) const { return dev >= 0 && dev < kMaxDevices && ((bits.load(std::memory_order_acquire) >> dev) & 1ull); }
+    void add(int dev) {
+        if (dev >= 0 && dev < kMaxDevices) bits.fetch_or(1ull << dev, std::memory_order_release);
+    }
+};
+// SM count of the current device (cached per ordinal; 0 if the query fails)
+inline int sm_count() {
+    static std::atomic<int> cache[kMaxDevices];
+    const int dev = current_device();
+    if (dev >= 0 && dev < kMaxDevices) {
+        const int c = cache[dev].load(std::memory_order_relaxed);
+        if (c > 0) return c;
+    }
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    if (dev >= 0 && dev < kMaxDevices) cache[dev].store(n, std::memory_order_relaxed);
+    return n;
+}
 
 // Launch with programmatic stream serialisation (programmatic dependent launch): the kernel may be scheduled while the
 // previous kernel of the stream is still draining, and synchronises with it through griddepcontrol.wait (ptx.cuh).
@@ -42,7 +76,8 @@ struct QuantArgs {
     int64_t strides[3][4];
     int S[3];
     int B, H, D;
-    float* amax_ws;
+    unsigned int* ctl;  // workspace words 0..7: generation of the last single-pass call, CTA check-in counter
+    float* cells;       // workspace + 8: amax cells of the two-pass kernels, then the single-pass kernel's slots
     int rows_per_cta;
     int force_two_pass;
     int given_scale;  // QA_SCALE_HEAD_GIVEN: scale[] is an input
@@ -68,6 +103,7 @@ struct AttnArgs {
     int v_dtype;
     int out_dtype;
     int qk_dtype;  // QA_DT_E4M3 (FP8 path) or QA_DT_BF16 / QA_DT_FP16 (16-bit path)
+    int64_t qs[3], ks[3], vs[3];  // element strides (batch, head, row) of q8 / k8 / v; the last dim is contiguous
 };
 
 struct MergeArgs {

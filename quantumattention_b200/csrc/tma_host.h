@@ -49,4 +49,22 @@ inline bool make_tmap_3d(CUtensorMap* out, CUtensorMapDataType dt, uint32_t elem
     return r == CUDA_SUCCESS;
 }
 
+// 4-D map over a [B, H, S, D] tensor with arbitrary (16-byte aligned) batch / head / row strides, D contiguous:
+// dims = {D, S, H, B}, box = [1, 1, box_rows, box_elems].  This is what lets the kernels consume a [B, S, H, D]-held
+// tensor (the usual layout of DiT / Llama projections) in place - the reference copies it dense first
+// (src/quantum_attn/tk/attention.py:419-421).
+inline bool make_tmap_4d(CUtensorMap* out, CUtensorMapDataType dt, const void* base, uint64_t row_elems, uint64_t n_rows,
+                         uint64_t n_heads, uint64_t n_batch, uint64_t row_stride_bytes, uint64_t head_stride_bytes,
+                         uint64_t batch_stride_bytes, uint32_t box_elems, uint32_t box_rows, CUtensorMapSwizzle swz) {
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) return false;
+    cuuint64_t dims[4] = {row_elems, n_rows, n_heads, n_batch};
+    cuuint64_t strides[3] = {row_stride_bytes, head_stride_bytes, batch_stride_bytes};
+    cuuint32_t box[4] = {box_elems, box_rows, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(out, dt, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
 }  // namespace qa

@@ -12,7 +12,7 @@ from typing import Optional
 import torch
 import torch.nn.functional as F
 
-from .nn import attention, can_use_attention, dynamically_quantize_fp8, fp8_attention
+from .nn import QuantizedKV, attention, can_use_attention, dynamically_quantize_fp8, fp8_attention, quantize_kv  # noqa: F401
 
 __all__ = [
     "attn_func",
@@ -54,10 +54,15 @@ def attn_func_with_fallback(query, key, value, attn_mask=None, dropout_p=0.0, is
 
 def fp8_attn_func(query, key, value, attn_mask: Optional[torch.Tensor] = None, dropout_p: float = 0.0,
                   is_causal: bool = False, *, scale: float = None, scale_q: Optional[torch.Tensor] = None,
-                  scale_k: Optional[torch.Tensor] = None, scaling_method: Optional[str] = None) -> torch.Tensor:
+                  scale_k: Optional[torch.Tensor] = None, scaling_method: Optional[str] = None,
+                  scale_v: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """The reference's signature (src/quantum_attn/quantum_attn_interface.py:101-113) plus one trailing optional
+    keyword: ``scale_v`` for a value tensor that was quantised ahead of time (``quantize_kv``; FP8 P modes).  The key
+    alone may come pre-quantised too (e4m3 ``key`` + ``scale_k`` with a 16-bit ``query``)."""
     return fp8_attention(
         query, key, value, attn_mask=attn_mask, dropout_p=dropout_p, is_causal=is_causal, scale=scale,
         scale_q=scale_q, scale_k=scale_k, scaling_method="head-wise" if scaling_method is None else scaling_method,
+        scale_v=scale_v,
     )
 
 
@@ -76,10 +81,11 @@ def fp8_attn_func_with_fallback(query, key, value, attn_mask=None, dropout_p=0.0
 def fp8_token_wise_attn_func(query, key, value, attn_mask: Optional[torch.Tensor] = None, dropout_p: float = 0.0,
                              is_causal: bool = False, *, scale: float = None,
                              scale_q: Optional[torch.Tensor] = None,
-                             scale_k: Optional[torch.Tensor] = None) -> torch.Tensor:
+                             scale_k: Optional[torch.Tensor] = None,
+                             scale_v: Optional[torch.Tensor] = None) -> torch.Tensor:
     return fp8_attention(
         query, key, value, attn_mask=attn_mask, dropout_p=dropout_p, is_causal=is_causal, scale=scale,
-        scale_q=scale_q, scale_k=scale_k, scaling_method="token-wise",
+        scale_q=scale_q, scale_k=scale_k, scaling_method="token-wise", scale_v=scale_v,
     )
 
 

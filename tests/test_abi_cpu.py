@@ -42,22 +42,35 @@ def test_argument_validation_without_gpu():
     assert rc == -1 and b"Unsupported head dimension: 96" in lib.qa_last_error()
     rc = lib.qa_quantize_fp8(4, one, 0, strides, one, one, None, 1, 1, S, 64, 1, None)
     assert rc == -1
-    rc = lib.qa_fp8_attn_fwd(16, 16, 16, 2, 16, 16, 16, 0, 16, 0, None, 1, 3, 2, 8, 8, 64, 0, 0.125, 0, None)
+    rc = lib.qa_fp8_attn_fwd(16, 16, 16, 2, None, None, None, 16, 16, 16, 0, 16, 0, None, 1, 3, 2, 8, 8, 64, 0, 0.125, 0, None)
     assert rc == -1 and b"multiple of Hkv" in lib.qa_last_error()
-    rc = lib.qa_fp8_attn_fwd(16, 16, 16, 0, 16, 16, None, 0, 16, 0, None, 1, 2, 2, 8, 8, 64, 0, 0.125, 0, None)
+    rc = lib.qa_fp8_attn_fwd(16, 16, 16, 0, None, None, None, 16, 16, None, 0, 16, 0, None, 1, 2, 2, 8, 8, 64, 0, 0.125, 0, None)
     assert rc == -1  # fp8 P mode with a 16-bit V
-    rc = lib.qa_attn_fwd(16, 16, 16, 2, 16, None, 1, 2, 2, 8, 8, 64, 0, 0.125, None)
+    rc = lib.qa_attn_fwd(16, 16, 16, 2, None, None, None, 16, None, 1, 2, 2, 8, 8, 64, 0, 0.125, None)
     assert rc == -1 and b"fp16 or bf16" in lib.qa_last_error()  # e4m3 inputs belong to qa_fp8_attn_fwd
-    rc = lib.qa_attn_fwd(16, 16, 16, 0, 16, None, 1, 2, 2, 8, 8, 96, 0, 0.125, None)
+    rc = lib.qa_attn_fwd(16, 16, 16, 0, None, None, None, 16, None, 1, 2, 2, 8, 8, 96, 0, 0.125, None)
     assert rc == -1 and b"Unsupported head dimension: 96" in lib.qa_last_error()
     import torch
 
     if not torch.cuda.is_available():
         # valid arguments but no device: must fail loudly, never fall back
         # (fake pointers: 16-byte aligned inputs, a 32-byte aligned output as the header asks)
-        rc = lib.qa_fp8_attn_fwd(16, 16, 16, 2, 16, 16, 16, 0, 32, 0, None, 1, 2, 2, 8, 8, 64, 0, 0.125, 0, None)
+        rc = lib.qa_fp8_attn_fwd(16, 16, 16, 2, None, None, None, 16, 16, 16, 0, 32, 0, None, 1, 2, 2, 8, 8, 64, 0, 0.125, 0, None)
         assert rc in (-2, -3)
-        rc = lib.qa_attn_fwd(16, 16, 16, 0, 32, None, 1, 2, 2, 8, 8, 64, 0, 0.125, None)
+        rc = lib.qa_attn_fwd(16, 16, 16, 0, None, None, None, 32, None, 1, 2, 2, 8, 8, 64, 0, 0.125, None)
         assert rc in (-2, -3)
-    rc = lib.qa_fp8_attn_fwd(16, 16, 16, 2, 16, 16, 16, 0, 16, 0, None, 1, 2, 2, 8, 8, 64, 0, 0.125, 0, None)
+    rc = lib.qa_fp8_attn_fwd(16, 16, 16, 2, None, None, None, 16, 16, 16, 0, 16, 0, None, 1, 2, 2, 8, 8, 64, 0, 0.125, 0, None)
     assert rc == -1 and b"32-byte aligned" in lib.qa_last_error()
+
+    # strides: every one a multiple of 16 bytes, the row stride at least the head dimension
+    bad = (ctypes.c_int64 * 3)(8 * 64 * 2, 8 * 64, 72)
+    rc = lib.qa_fp8_attn_fwd(16, 16, 16, 2, bad, None, None, 16, 16, 16, 0, 32, 0, None, 1, 2, 2, 8, 8, 64, 0, 0.125, 0,
+                             None)
+    assert rc == -1 and b"multiple of 16 bytes" in lib.qa_last_error()
+    # the one-call entry point validates like the two it combines
+    rc = lib.qa_fp8_attn_func(16, 16, 16, 0, None, None, None, 16, 16, None, 16, 16, None, 16, 0, 32, None,
+                              1, 2, 2, 8, 8, 96, 0, 0.125, 0, 2, None)
+    assert rc == -1 and b"Unsupported head dimension: 96" in lib.qa_last_error()
+    rc = lib.qa_fp8_attn_func(16, 16, 16, 0, None, None, None, 16, 16, None, 16, 16, None, 16, 0, 32, None,
+                              1, 2, 2, 8, 8, 64, 0, 0.125, 0, 0, None)
+    assert rc == -1 and b"v8 and scale_v" in lib.qa_last_error()

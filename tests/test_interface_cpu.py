@@ -17,8 +17,13 @@ def test_public_surface_matches_reference():
     for n in quantum_attn.__all__:
         assert callable(getattr(quantum_attn, n)) and callable(getattr(quantum_attn_interface, n))
     sig = inspect.signature(quantum_attn.fp8_attn_func)
-    assert list(sig.parameters) == ["query", "key", "value", "attn_mask", "dropout_p", "is_causal", "scale",
-                                    "scale_q", "scale_k", "scaling_method"]
+    # the reference's parameters, in its order (src/quantum_attn/quantum_attn_interface.py:101-113); anything beyond them
+    # must be an optional trailing keyword (scale_v: a value tensor quantised ahead of time)
+    ref_params = ["query", "key", "value", "attn_mask", "dropout_p", "is_causal", "scale", "scale_q", "scale_k",
+                  "scaling_method"]
+    assert list(sig.parameters)[:len(ref_params)] == ref_params
+    for extra in list(sig.parameters)[len(ref_params):]:
+        assert sig.parameters[extra].kind is inspect.Parameter.KEYWORD_ONLY and sig.parameters[extra].default is None
     assert sig.parameters["scale"].kind is inspect.Parameter.KEYWORD_ONLY
     sig = inspect.signature(quantum_attn.fp8_token_wise_attn_func)
     assert "scaling_method" not in sig.parameters
@@ -84,3 +89,55 @@ def test_fake_tensor_shapes():
         assert out.shape == (2, 4, 100, 128) and out.dtype == torch.float16
         t8, sc = quantum_attn.dynamically_quantize_fp8(v, reduction_dim=-1)
         assert t8.dtype == torch.float8_e4m3fn and sc.shape == (2, 4, 77)
+
+
+def test_traced_graph_holds_the_native_ops_only():
+    """dynamo trace (no GPU needed: the backend only looks at the graph): fp8_attn_func becomes ONE graph of the native
+    quantiser op + the reference-named attention op - no aten arithmetic that Inductor would turn into its own
+    kernels (the reference's graph holds its aten quantiser there, src/quantum_attn/nn.py:14-19,410-418)."""
+    class Stop(Exception):
+        pass
+
+    seen = []
+
+    def backend(gm, example_inputs):
+        seen.append([str(n.target) for n in gm.graph.nodes if n.op == "call_function"])
+
+        def run(*a):
+            raise Stop()
+        return run
+
+    q = torch.randn(1, 2, 64, 64, dtype=torch.bfloat16)
+    for fn, kw in ((quantum_attn.fp8_attn_func, {"is_causal": True}), (quantum_attn.fp8_token_wise_attn_func, {}),
+                   (lambda a, b, c: quantum_attn.dynamically_quantize_fp8(a, reduction_dim=[2, 3]), {})):
+        torch._dynamo.reset()
+        seen.clear()
+        with quantum_attn.config.patch({"attention.skip_supported_check": True}):
+            with pytest.raises(Stop):
+                torch.compile(fn, backend=backend, fullgraph=True)(q, q, q, **kw)
+        assert len(seen) == 1
+        names = seen[0]
+        assert all(n.startswith("quantum_attn.") or "getitem" in n for n in names), names
+        assert any("quantize" in n for n in names), names
+
+
+def test_scale_shape_rules():
+    from quantum_attn import nn, ops
+    from quantumattention_b200 import _native
+
+    q8 = torch.zeros(2, 3, 10, 64, dtype=torch.float8_e4m3fn)
+    k8 = torch.zeros(2, 3, 12, 64, dtype=torch.float8_e4m3fn)
+    assert ops._scale_mode_of(torch.ones(2, 3), q8, torch.ones(2, 3), k8) == _native.QA_SCALE_HEAD
+    assert ops._scale_mode_of(torch.ones(2, 3, 10), q8, torch.ones(2, 3, 12), k8) == _native.QA_SCALE_TOKEN
+    with pytest.raises(ValueError, match="granularity"):
+        ops._scale_mode_of(torch.ones(2, 3), q8, torch.ones(2, 3, 12), k8)
+    with pytest.raises(ValueError, match="matches neither"):
+        ops._scale_mode_of(torch.ones(2, 3, 11), q8)
+    v = nn._validate_input
+    q = torch.randn(2, 3, 10, 64, dtype=torch.bfloat16)
+    # a tensor is pre-quantised exactly when its scale comes with it; the key alone may be
+    assert "scale_q and scale_k" in v(q, q, q, scaling_method="head-wise", scale_q=torch.ones(2, 3), scale_k=torch.ones(2, 3))[1]
+    assert "scale_q and scale_k" in v(q8, k8, q, scaling_method="head-wise")[1]
+    assert "CUDA device" in v(q, k8, q, scaling_method="head-wise", scale_k=torch.ones(2, 3))[1]  # passes the dtype rules
+    assert "scale_v" in v(q, q, q8, scaling_method="head-wise")[1]
+    assert "scale_v" in v(q, q, q, scaling_method="head-wise", scale_v=torch.ones(2, 3))[1]
