@@ -170,6 +170,15 @@ int qa_attn_fwd(const void* q, const void* k, const void* v, int dtype, const in
 int qa_merge_partials(float* o_acc, float* lse_acc, const void* o_new, int o_dtype, const float* lse_new, void* out,
                       long long rows, int D, int first, void* stream);
 
+/* Strided block copy on the copy engines: `rows` rows of `width_bytes`, row r from src + r * src_pitch to
+ * dst + r * dst_pitch (cudaMemcpy2DAsync, direction inferred from the addresses).  The sequence-sharded path pulls the
+ * other ranks' e4m3 K / V blocks with it straight from PEER memory (buffers mapped through CUDA IPC / symmetric
+ * memory) into the per-head layout the fused kernel reads: the transfer crosses NVLink without occupying an SM, so
+ * it overlaps the attention kernel completely - a collective kernel would take SMs away from it.  New operator (the
+ * reference never shards a sequence).  Asynchronous on `stream`; launches no kernel. */
+int qa_copy_2d(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes, size_t rows,
+               void* stream);
+
 /* Number of kernels the previous call on this thread launched (for bench.py's gpu_launches accounting). */
 int qa_last_launch_count(void);
 

@@ -30,6 +30,7 @@ EXPORTED_SYMBOLS = (
     "qa_fp8_attn_func",
     "qa_attn_fwd",
     "qa_merge_partials",
+    "qa_copy_2d",
     "qa_last_launch_count",
 )
 
@@ -97,6 +98,8 @@ def load(build_if_missing: bool = True):
         lib.qa_merge_partials.argtypes = [vp, vp, vp, ctypes.c_int, vp, vp, ctypes.c_longlong, ctypes.c_int,
                                           ctypes.c_int, vp]
         lib.qa_merge_partials.restype = ctypes.c_int
+        lib.qa_copy_2d.argtypes = [vp, ctypes.c_size_t, vp, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, vp]
+        lib.qa_copy_2d.restype = ctypes.c_int
         if lib.qa_abi_version() != ABI_VERSION:
             raise NativeError(f"ABI mismatch: library {lib.qa_abi_version()} != binding {ABI_VERSION}")
         _lib = lib
@@ -202,14 +205,16 @@ def _strided(t: torch.Tensor):
 
 def quantize_fp8(tensors: Sequence[torch.Tensor], scale_mode: int,
                  scales: Optional[Sequence[torch.Tensor]] = None,
-                 workspace: Optional[torch.Tensor] = None) -> Tuple[list, list]:
+                 workspace: Optional[torch.Tensor] = None,
+                 outs: Optional[Sequence[torch.Tensor]] = None) -> Tuple[list, list]:
     """Quantise 1-3 CUDA tensors [B,H,S_i,D] (bf16/fp16, same B,H,D,dtype) in one launch pair.
 
     Returns ([e4m3 tensors], [fp32 scales: [B,H] head-wise or [B,H,S_i] token-wise]).
     ``workspace``: optional caller-owned scratch (plain contract: contents ignored); by default a per-(device, stream)
     workspace under the QA_WS_PERSISTENT contract is used, which saves the per-call clear.
     ``QA_SCALE_HEAD_AMAX_ONLY`` returns ([], scales) without quantising; ``QA_SCALE_HEAD_GIVEN`` quantises with the
-    fp32 [B,H] ``scales`` passed in.
+    fp32 [B,H] ``scales`` passed in.  ``outs``: optional dense e4m3 / uint8 destinations of the inputs' shapes (e.g.
+    views of a peer-visible communication buffer).
     """
     lib = load()
     n = len(tensors)
@@ -226,7 +231,15 @@ def quantize_fp8(tensors: Sequence[torch.Tensor], scale_mode: int,
         xs.append(t)
     amax_only = scale_mode == QA_SCALE_HEAD_AMAX_ONLY
     with _on_device(idx):
-        outs = [] if amax_only else [torch.empty(t.shape, dtype=torch.float8_e4m3fn, device=dev) for t in xs]
+        if amax_only:
+            outs = []
+        elif outs is None:
+            outs = [torch.empty(t.shape, dtype=torch.float8_e4m3fn, device=dev) for t in xs]
+        else:
+            outs = list(outs)
+            if len(outs) != n or any(o.shape != t.shape or o.element_size() != 1 or not o.is_contiguous() or o.device != dev
+                                     for o, t in zip(outs, xs)):
+                raise ValueError("quantize_fp8: `outs` must be dense 1-byte tensors of the inputs' shapes and device")
         if scale_mode == QA_SCALE_HEAD_GIVEN:
             if scales is None or len(scales) != n:
                 raise ValueError("quantize_fp8: QA_SCALE_HEAD_GIVEN needs one [B,H] fp32 scale tensor per input")
@@ -271,9 +284,10 @@ def _f32c(t: Optional[torch.Tensor]):
 
 def fp8_attn_fwd(q8: torch.Tensor, k8: torch.Tensor, v: torch.Tensor, scale_q: torch.Tensor, scale_k: torch.Tensor,
                  scale_v: Optional[torch.Tensor], *, scale_mode: int, is_causal: bool, sm_scale: float, p_mode: int,
-                 out_dtype: torch.dtype, return_lse: bool = False):
+                 out_dtype: torch.dtype, return_lse: bool = False, out: Optional[torch.Tensor] = None):
     """Launch the fused forward kernel.  q8/k8 e4m3 [B,H,S,D]; v e4m3 (+scale_v) or bf16/fp16.  Tensors whose last
-    dim is contiguous and whose strides are 16-byte multiples ([B,S,H,D]-held views) are read in place."""
+    dim is contiguous and whose strides are 16-byte multiples ([B,S,H,D]-held views) are read in place.  ``out``:
+    optional dense [B,Hq,Sq,D] destination (e.g. a head range of a larger output)."""
     lib = load()
     B, Hq, Sq, D = q8.shape
     Hkv, Skv = k8.shape[1], k8.shape[2]
@@ -287,8 +301,12 @@ def fp8_attn_fwd(q8: torch.Tensor, k8: torch.Tensor, v: torch.Tensor, scale_q: t
         raise ValueError(f"scale_v must have B*Hkv = {B * Hkv} elements")
     (q8, qs), (k8, ks), (v, vs) = _strided(q8), _strided(k8), _strided(v)
     scale_q, scale_k, scale_v = _f32c(scale_q), _f32c(scale_k), _f32c(scale_v)
+    if out is not None and (out.shape != (B, Hq, Sq, D) or out.dtype != out_dtype or not out.is_contiguous()
+                            or out.device != dev):
+        raise ValueError("fp8_attn_fwd: `out` must be a dense [B,Hq,Sq,D] tensor of out_dtype on the inputs' device")
     with _on_device(idx):
-        out = torch.empty((B, Hq, Sq, D), dtype=out_dtype, device=dev)
+        if out is None:
+            out = torch.empty((B, Hq, Sq, D), dtype=out_dtype, device=dev)
         lse = torch.empty((B, Hq, Sq), dtype=torch.float32, device=dev) if return_lse else None
         stream = _raw_stream(idx)
         if attn_events is not None:
@@ -423,3 +441,8 @@ def merge_partials(o_acc: Optional[torch.Tensor], lse_acc: torch.Tensor, o_new: 
     _check(rc, "qa_merge_partials")
     global launch_total
     launch_total += int(lib.qa_last_launch_count())
+
+
+def copy_2d(dst_ptr: int, dst_pitch: int, src_ptr: int, src_pitch: int, width_bytes: int, rows: int, stream: int) -> None:
+    """Asynchronous strided block copy on the copy engines (``qa_copy_2d``); raw device addresses and a raw stream."""
+    _check(load().qa_copy_2d(dst_ptr, dst_pitch, src_ptr, src_pitch, width_bytes, rows, stream), "qa_copy_2d")

@@ -291,6 +291,20 @@ int qa_attn_fwd(const void* q, const void* k, const void* v, int dtype, const in
     return attn16_fwd_dispatch(a, static_cast<cudaStream_t>(stream), &g_launches);
 }
 
+int qa_copy_2d(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes, size_t rows,
+               void* stream) {
+    g_launches = 0;
+    if (!dst || !src) return set_error(QA_ERR_INVALID, "null pointer argument");
+    if (width_bytes == 0 || rows == 0) return QA_OK;
+    if (dst_pitch < width_bytes || src_pitch < width_bytes) return set_error(QA_ERR_INVALID, "pitch smaller than the row width");
+    // cudaMemcpyDefault: source and destination are told apart by their addresses (unified addressing), so a
+    // peer-mapped source makes this a copy-engine transfer over NVLink that occupies no SM
+    cudaError_t e = cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width_bytes, rows, cudaMemcpyDefault,
+                                      static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return set_cuda_error("cudaMemcpy2DAsync", e);
+    return QA_OK;
+}
+
 int qa_merge_partials(float* o_acc, float* lse_acc, const void* o_new, int o_dtype, const float* lse_new, void* out,
                       long long rows, int D, int first, void* stream) {
     g_launches = 0;

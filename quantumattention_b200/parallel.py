@@ -6,13 +6,17 @@ src/quantum_attn/tk/attention.py:417,465); callers such as ParaAttention shard t
 * **head sharding** - every (batch, head) is an independent problem (the kernel's grid y/z axes,
   src/quantum_attn/tk/attention.py:504; head-wise scales are per (b, h), src/quantum_attn/nn.py:411-412), so ranks
   take contiguous head ranges and there is NO collective: ``shard_heads`` / ``head_sharded_fp8_attention``.
-* **sequence ring** for shapes whose single (b, h) problems are too long for one GPU's share of the latency budget
-  (BASELINE config 4, S = 75 600): each rank owns S/N tokens of Q, K and V.  Q, K, V are quantised ONCE to e4m3 with
-  head scales made global by a single ``all_reduce(MAX)`` (12*B*H bytes) - so the bytes are the ones the unsharded
-  call would produce - and the e4m3 K/V blocks (half the bytes of the 16-bit tensors) reach the other ranks either by
-  ONE all-gather over NVSwitch that runs under the attention of the local block (default; two launches and one merge
-  whatever the world size) or round a neighbour ring with ``batch_isend_irecv`` while the fused kernel attends the
-  block already here.  Partial results carry their log-sum-exp and are combined by ``qa_merge_partials``.
+* **sequence sharding** for shapes whose single (b, h) problems are too long for one GPU's share of the latency budget
+  (BASELINE config 4, S = 75 600): each rank owns S/N tokens of Q, K and V.  Q and K (and V in the FP8 P modes) are
+  quantised ONCE to e4m3 with head scales made global by a single ``all_reduce(MAX)`` (<= 12*B*H bytes) - so the bytes
+  are the ones the unsharded call would produce, in EVERY P mode including the default "16bit" (e4m3 K and 16-bit V on
+  the wire: the reference's numerics, inside the 2e-2 bound).  Strategy ``gather`` (default): the K / V blocks of
+  all ranks are laid end to end PER HEAD in local memory, a few heads at a time, and each group of heads is attended
+  in one launch over all keys as soon as its blocks are there - no partial results, no merge, no re-layout copy.  The
+  blocks travel either by grouped NCCL all-gathers (``transport="nccl"``) or - ``transport="peer"`` - are PULLED from
+  the other ranks' peer-mapped buffers by the copy engines (``qa_copy_2d``), which crosses NVSwitch without taking
+  an SM from the attention kernel.  Strategy ``ring``: neighbour ``batch_isend_irecv`` while the fused kernel attends
+  the block already here, partial results combined through their log-sum-exp by ``qa_merge_partials``.
   Non-causal only (as the BASELINE config).
 
 The kernels are reached through a small backend object so that the host logic (ring order, buffer rotation, scale
@@ -69,7 +73,7 @@ def head_sharded_fp8_attention(q, k, v, *, is_causal=False, scale=None, scaling_
     return torch.cat(parts, dim=1)
 
 
-# ------------------------------------------------------------------------------------------------ sequence ring
+# ------------------------------------------------------------------------------------------------ sequence sharding
 class NativeBackend:
     """The sm_100a kernels (include/qattn.h).  Raises if the library or the device is missing."""
 
@@ -77,13 +81,13 @@ class NativeBackend:
         _, scales = _native.quantize_fp8(list(tensors), _native.QA_SCALE_HEAD_AMAX_ONLY)
         return scales
 
-    def quantize(self, tensors: Sequence[torch.Tensor], scales: Sequence[torch.Tensor]) -> List[torch.Tensor]:
-        outs, _ = _native.quantize_fp8(list(tensors), _native.QA_SCALE_HEAD_GIVEN, scales=list(scales))
+    def quantize(self, tensors: Sequence[torch.Tensor], scales: Sequence[torch.Tensor], outs=None) -> List[torch.Tensor]:
+        outs, _ = _native.quantize_fp8(list(tensors), _native.QA_SCALE_HEAD_GIVEN, scales=list(scales), outs=outs)
         return outs
 
-    def attend(self, q8, k8, v8, sq, sk, sv, sm_scale, p_mode, out_dtype):
-        return _native.fp8_attn_fwd(q8, k8, v8, sq, sk, sv, scale_mode=_native.QA_SCALE_HEAD, is_causal=False,
-                                    sm_scale=sm_scale, p_mode=p_mode, out_dtype=out_dtype, return_lse=True)
+    def attend(self, q8, k8, v, sq, sk, sv, sm_scale, p_mode, out_dtype, out=None, return_lse=True):
+        return _native.fp8_attn_fwd(q8, k8, v, sq, sk, sv, scale_mode=_native.QA_SCALE_HEAD, is_causal=False,
+                                    sm_scale=sm_scale, p_mode=p_mode, out_dtype=out_dtype, return_lse=return_lse, out=out)
 
     def merge(self, o_acc, lse_acc, o_new, lse_new, first, out=None):
         _native.merge_partials(o_acc, lse_acc, o_new, lse_new, first=first, out=out)
@@ -97,62 +101,177 @@ def _ring_exchange(send_buf: torch.Tensor, recv_buf: torch.Tensor, group) -> lis
     return dist.batch_isend_irecv(ops_)
 
 
-SEQ_STRATEGIES = ("ring", "gather")
+SEQ_STRATEGIES = ("gather", "ring")
+SEQ_TRANSPORTS = ("nccl", "peer")
 
 
 def seq_pv_mode() -> str:
-    """P mode of the sequence-sharded path when the caller names none: the configured one, except that the library
-    default "16bit" (V stays 16-bit) cannot apply - e4m3 K/V on the wire is the point of this path - and maps to
-    "fp8"; ask for "fp8_hilo" to stay inside the 2e-2 max-abs bound."""
+    """P mode of the sequence-sharded path when the caller names none: the configured one - by default "16bit", the
+    reference's numerics (e4m3 K and 16-bit V travel), which meets the 2e-2 max-abs bound like the one-GPU call."""
     from . import config
 
-    return "fp8" if config.attention.pv_mode == "16bit" else config.attention.pv_mode
+    return config.attention.pv_mode
 
 
 def default_seq_strategy() -> str:
-    """``QA_SEQ_STRATEGY`` (ring | gather), else the measured choice."""
+    """``QA_SEQ_STRATEGY`` (gather | ring), else the measured choice."""
     s = os.environ.get("QA_SEQ_STRATEGY", "gather")
     if s not in SEQ_STRATEGIES:
         raise ValueError(f"QA_SEQ_STRATEGY must be one of {SEQ_STRATEGIES} but got {s!r}")
     return s
 
 
-def _gather_blocks(kv_loc: torch.Tensor, world: int, group):
-    """Start the all-gather of every rank's [2,B,H,S,D] e4m3 K/V block; returns ([world,2,B,H,S,D] bytes, work)."""
-    # (the gloo backend of the CPU tests wants the output as a dim-0 concatenation of the inputs)
-    flat = torch.empty((world * kv_loc.shape[0],) + tuple(kv_loc.shape[1:]), dtype=kv_loc.dtype, device=kv_loc.device)
-    work = dist.all_gather_into_tensor(flat, kv_loc, group=group, async_op=True)
-    return flat.view((world,) + tuple(kv_loc.shape)), work
+def default_seq_transport() -> str:
+    """``QA_SEQ_TRANSPORT`` (nccl | peer), else the default."""
+    s = os.environ.get("QA_SEQ_TRANSPORT", _DEFAULT_TRANSPORT)
+    if s not in SEQ_TRANSPORTS:
+        raise ValueError(f"QA_SEQ_TRANSPORT must be one of {SEQ_TRANSPORTS} but got {s!r}")
+    return s
 
 
-def _concat_other_blocks(kv_all: torch.Tensor, rank: int) -> torch.Tensor:
-    """[world,2,B,H,S,D] gathered bytes -> [2,B,H,(world-1)*S,D]: the keys / values of every OTHER rank laid end to
-    end per head (key order is immaterial to non-causal attention).  Two strided copies of 8-byte words."""
-    world, two, B, H, S, D = kv_all.shape
-    dst = torch.empty((two, B, H, (world - 1) * S, D), dtype=kv_all.dtype, device=kv_all.device)
-    wide = torch.int64 if D % 8 == 0 else kv_all.dtype
-    src6 = kv_all.view(wide).permute(1, 2, 3, 0, 4, 5)  # [2,B,H,world,S,D/8]
-    dst6 = dst.view(wide).view(two, B, H, world - 1, S, -1)
-    if rank > 0:
-        dst6[:, :, :, :rank].copy_(src6[:, :, :, :rank])
-    if rank < world - 1:
-        dst6[:, :, :, rank:].copy_(src6[:, :, :, rank + 1:])
-    return dst
+_DEFAULT_TRANSPORT = "nccl"
+
+
+def head_chunks(B: int, H: int, S_local: int, n_sms: int = 148, max_chunks: int = 12) -> List[Tuple[int, int]]:
+    """Head ranges [lo, hi) the gather strategy moves and attends one after the other.  A launch over ``hc`` heads has
+    B * hc * ceil(S_local / 256) CTAs (two 128-row query tiles per CTA, one CTA per SM).  ``hc`` is the SMALLEST head
+    count (most groups, so the transfer of group i + 1 hides under the attention of group i and the exposed first
+    transfer is short) among those whose launch wastes the least of its last wave - no launch then pays more wave
+    quantisation than a single launch over all heads would.  At most ``max_chunks`` groups."""
+    ctas_per_head = max(1, B * ((S_local + 255) // 256))
+    best = None
+    for hc in range(1, H + 1):
+        if -(-H // hc) > max_chunks:
+            continue
+        n = hc * ctas_per_head
+        waste = round((-(-n // n_sms) * n_sms) / n, 2)  # SM-slots paid per SM-slot used (1.0 = whole waves)
+        if best is None or waste < best[0]:
+            best = (waste, hc)
+    hc = best[1] if best else H
+    return [(lo, min(H, lo + hc)) for lo in range(0, H, hc)]
+
+
+class _Works:
+    """wait() on a set of async collectives (one coalesced work, or several plain ones)."""
+
+    def __init__(self, works):
+        self.works = [w for w in works if w is not None]
+
+    def wait(self):
+        for w in self.works:
+            w.wait()
+
+
+def _nccl_gather_heads(srcs: Sequence[torch.Tensor], dsts: Sequence[torch.Tensor], lo: int, hi: int, group) -> _Works:
+    """All-gather heads [lo, hi) of every ``src`` [B,H,S,*] into ``dst`` [B,H,world*S,*]: per (b, h) the blocks of all
+    ranks end to end in rank order.  One all-gather per (tensor, b, h) - each a contiguous S x row chunk on both
+    sides - issued as ONE grouped NCCL call where the backend can coalesce them."""
+    pairs = []
+    for src, dst in zip(srcs, dsts):
+        for b in range(src.shape[0]):
+            for h in range(lo, hi):
+                pairs.append((dst[b, h].view(torch.uint8), src[b, h].view(torch.uint8)))
+    if srcs[0].is_cuda:
+        with dist._coalescing_manager(group=group, async_ops=True) as cm:
+            for o, i in pairs:
+                dist.all_gather_into_tensor(o, i, group=group)
+        return _Works([cm])
+    # (gloo, CPU tests: no coalesced all-gather; same data movement, one collective each)
+    return _Works([dist.all_gather_into_tensor(o, i, group=group, async_op=True) for o, i in pairs])
+
+
+class PeerGather:
+    """Copy-engine gather over NVSwitch peer memory.  Every rank keeps its outgoing K / V blocks in a symmetric-memory
+    buffer (mapped into every peer's address space through CUDA IPC by ``torch.distributed._symmetric_memory``); after
+    a device-side barrier each rank PULLS the other ranks' blocks into its own per-head layout with strided copies on
+    a side stream (``qa_copy_2d``: cudaMemcpy2DAsync from the peer pointer).  No kernel is launched for the transfer.
+    Two send slots alternate so that one barrier per call suffices: a peer still reading slot p of call i has finished
+    before it reaches the barrier of call i + 1, and slot p is next written in call i + 2."""
+
+    _cache = {}
+
+    @classmethod
+    def get(cls, group, device, k_shape, v_shape, v_itemsize):
+        key = (id(group) if group is not None else 0, device.index, tuple(k_shape), tuple(v_shape), v_itemsize)
+        obj = cls._cache.get(key)
+        if obj is None:
+            obj = cls._cache[key] = cls(group, device, k_shape, v_shape, v_itemsize)
+        return obj
+
+    def __init__(self, group, device, k_shape, v_shape, v_itemsize):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        pg = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(pg), dist.get_rank(pg)
+        self.device = device
+        self.nk = int(torch.Size(k_shape).numel())
+        self.nv = int(torch.Size(v_shape).numel()) * v_itemsize
+        self.slot = (self.nk + self.nv + 255) // 256 * 256
+        try:
+            symm_mem.enable_symm_mem_for_group(pg.group_name)
+        except Exception:
+            pass
+        self.buf = symm_mem.empty(2 * self.slot, dtype=torch.uint8, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, pg)
+        self.peers = [self.hdl.get_buffer(r, (2 * self.slot,), torch.uint8, 0) for r in range(self.world)]
+        self.stream = torch.cuda.Stream(device=device)
+        self.phase = 0
+        B, H, S, D = k_shape
+        self.k_all = torch.empty((B, H, self.world * S, D), dtype=torch.uint8, device=device)
+        self.v_all = torch.empty((B, H, self.world * S, D * v_itemsize), dtype=torch.uint8, device=device)
+
+    def send_views(self, k_shape, v_shape, v_itemsize):
+        """This call's slot of the local symmetric buffer as (k8 bytes [B,H,S,D], v bytes [B,H,S,D*itemsize])."""
+        base = self.phase * self.slot
+        kb = self.buf[base:base + self.nk].view(k_shape)
+        vb = self.buf[base + self.nk:base + self.nk + self.nv].view(tuple(v_shape[:-1]) + (v_shape[-1] * v_itemsize,))
+        return kb, vb
+
+    def pull(self, chunks: Sequence[Tuple[int, int]]) -> List[torch.cuda.Event]:
+        """Barrier, then start the pulls for every head group; returns one event per group (its blocks have landed)."""
+        main = torch.cuda.current_stream(self.device)
+        self.hdl.barrier(channel=self.phase)  # every rank's blocks of this call are in its slot
+        self.stream.wait_stream(main)
+        raw = self.stream.cuda_stream
+        B, H, S_all, D = self.k_all.shape
+        S = S_all // self.world
+        Dv = self.v_all.shape[-1]
+        base = self.phase * self.slot
+        events = []
+        for lo, hi in chunks:
+            for i in range(self.world):
+                r = (self.rank + i) % self.world  # own block first (local copy), then the peers, each rank another order
+                src = self.peers[r].data_ptr() + base
+                for b in range(B):
+                    # K: rows = heads of the group; a row is this rank-block of one head, S x D bytes
+                    _native.copy_2d(self.k_all.data_ptr() + ((b * H + lo) * S_all + r * S) * D, S_all * D,
+                                    src + (b * H + lo) * S * D, S * D, S * D, hi - lo, raw)
+                    _native.copy_2d(self.v_all.data_ptr() + ((b * H + lo) * S_all + r * S) * Dv, S_all * Dv,
+                                    src + self.nk + (b * H + lo) * S * Dv, S * Dv, S * Dv, hi - lo, raw)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+            events.append(ev)
+        self.phase ^= 1
+        return events
 
 
 def ring_fp8_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: Optional[float] = None,
                        pv_mode: Optional[str] = None, group=None, backend=None,
-                       strategy: Optional[str] = None) -> torch.Tensor:
+                       strategy: Optional[str] = None, transport: Optional[str] = None,
+                       head_groups: Optional[int] = None) -> torch.Tensor:
     """Non-causal FP8 attention over a sequence sharded across the ranks of ``group``.
 
     q, k, v: this rank's [B, H, S_local, D] 16-bit slices (equal S_local on every rank); returns the [B, H, S_local, D]
     output rows of the local queries against the keys/values of ALL ranks.  With world size 1 this is exactly
-    ``fp8_attn_func(q, k, v)`` in the chosen P mode (``seq_pv_mode()`` when none is given).
+    ``fp8_attn_func(q, k, v)`` in the chosen P mode (the configured one when none is given; every mode is supported:
+    in "16bit" the value blocks travel in 16 bits).
 
-    ``strategy``: how the other ranks' e4m3 K/V reach this one.  "ring": world - 1 neighbour exchanges, one kernel launch
-    and one merge per block.  "gather": ONE all-gather over NVSwitch (every GPU has full bandwidth to every peer, so
-    nothing is won by forwarding hop by hop) that overlaps the attention of the local block, then ONE launch over all
-    the other ranks' keys and one merge - two launches whatever the world size.  Same quantised bytes either way.
+    ``strategy`` "gather" (default): per group of heads, all ranks' K / V blocks are laid end to end in local memory
+    and attended in ONE launch over all keys - no partial results; group i + 1 travels while group i is attended.
+    ``transport`` chooses how they travel: "nccl" (grouped all-gathers) or "peer" (copy-engine pulls from peer-mapped
+    symmetric memory; no SM is spent on communication).  ``head_groups`` overrides the number of head groups
+    (default: ``head_chunks``).  ``strategy`` "ring": world - 1 neighbour exchanges, one launch and one (O, LSE) merge
+    per block.  Same quantised bytes every way.
     """
     be = backend if backend is not None else NativeBackend()
     world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -162,47 +281,86 @@ def ring_fp8_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, sca
     if pv_mode is None:
         pv_mode = seq_pv_mode()
     p_mode = ops.pv_mode_code(pv_mode)
-    if p_mode == _native.QA_P_16BIT:
-        raise ValueError("ring_fp8_attention moves e4m3 K/V blocks: pv_mode must be 'fp8' or 'fp8_hilo'")
+    v16 = p_mode == _native.QA_P_16BIT
     strategy = default_seq_strategy() if strategy is None else strategy
     if strategy not in SEQ_STRATEGIES:
         raise ValueError(f"strategy must be one of {SEQ_STRATEGIES} but got {strategy!r}")
+    transport = default_seq_transport() if transport is None else transport
+    if transport not in SEQ_TRANSPORTS:
+        raise ValueError(f"transport must be one of {SEQ_TRANSPORTS} but got {transport!r}")
     B, H, S, D = q.shape
     sm_scale = (1.0 / math.sqrt(D)) if scale is None else float(scale)
 
     # 1. head scales of the WHOLE sequence: local scales, one MAX all-reduce (scale is monotone in amax)
-    scales = torch.stack(be.local_scales([q, k, v]))  # [3, B, H] fp32
+    scales = torch.stack(be.local_scales([q, k] if v16 else [q, k, v]))  # [2 or 3, B, H] fp32
     if world > 1:
         dist.all_reduce(scales, op=dist.ReduceOp.MAX, group=group)
-    sq, sk, sv = scales[0], scales[1], scales[2]
-    # 2. quantise once; K and V share one buffer so a ring step is one send and one receive
-    q8, k8, v8 = be.quantize([q, k, v], [sq, sk, sv])
-    kv = [torch.stack((k8.view(torch.uint8), v8.view(torch.uint8))), None]  # [2, B, H, S, D] bytes
-    if world > 1 and strategy == "ring":
-        kv[1] = torch.empty_like(kv[0])
-
+    sq, sk, sv = scales[0], scales[1], (None if v16 else scales[2])
     out = torch.empty_like(q)
-    o_acc = torch.empty((B, H, S, D), dtype=torch.float32, device=q.device) if world > 1 else None
-    lse_acc = torch.empty((B, H, S), dtype=torch.float32, device=q.device)
-    if strategy == "gather" and world > 1:
-        kv_all, work = _gather_blocks(kv[0], world, group)
-        # the local block needs nothing from the wire: attend it while the gather runs
-        o_new, lse_new = be.attend(q8, k8, v8, sq, sk, sv, sm_scale, p_mode, q.dtype)
-        be.merge(o_acc, lse_acc, o_new, lse_new, True, None)
-        work.wait()
-        rest = _concat_other_blocks(kv_all, rank)
-        del kv_all
-        o_new, lse_new = be.attend(q8, rest[0].view(torch.float8_e4m3fn), rest[1].view(torch.float8_e4m3fn), sq, sk, sv,
-                                   sm_scale, p_mode, q.dtype)
-        be.merge(o_acc, lse_acc, o_new, lse_new, False, out)
+
+    if world == 1:
+        q8, k8 = be.quantize([q, k], [sq, sk])
+        v_in = v if v16 else be.quantize([v], [sv])[0]
+        be.attend(q8, k8, v_in, sq, sk, sv, sm_scale, p_mode, q.dtype, out=out, return_lse=False)
         return out
+
+    if strategy == "gather":
+        # 2. K / V first - they travel - then Q while the first blocks are on the wire
+        if head_groups is None:
+            chunks = head_chunks(B, H, S)
+        else:  # caller's choice (tests; tuning)
+            hc = -(-H // max(1, min(H, int(head_groups))))
+            chunks = [(lo, min(H, lo + hc)) for lo in range(0, H, hc)]
+        f8 = torch.float8_e4m3fn
+        if transport == "peer":
+            comm = PeerGather.get(group, q.device, k.shape, v.shape, v.element_size() if v16 else 1)
+            kb, vb = comm.send_views(k.shape, v.shape, v.element_size() if v16 else 1)
+            if v16:
+                be.quantize([k], [sk], outs=[kb])
+                vb.view(v.dtype).copy_(v)
+            else:
+                be.quantize([k, v], [sk, sv], outs=[kb, vb])
+            waits = comm.pull(chunks)
+            k_all = comm.k_all.view(f8)
+            v_all = comm.v_all.view(v.dtype if v16 else f8)
+            wait = lambda w: torch.cuda.current_stream(q.device).wait_event(w)
+        else:
+            if v16:
+                (k8,) = be.quantize([k], [sk])
+                v_send = v.contiguous()
+            else:
+                k8, v_send = be.quantize([k, v], [sk, sv])
+            k_all = torch.empty((B, H, world * S, D), dtype=f8, device=q.device)
+            v_all = torch.empty((B, H, world * S, D), dtype=v_send.dtype, device=q.device)
+            waits = [_nccl_gather_heads([k8, v_send], [k_all, v_all], lo, hi, group) for lo, hi in chunks]
+            wait = lambda w: w.wait()
+        (q8,) = be.quantize([q], [sq])
+        # 3. one launch per head group over ALL keys, as its blocks land
+        for (lo, hi), w in zip(chunks, waits):
+            wait(w)
+            dst = out[:, lo:hi] if B == 1 else None  # (a head range of a [1,H,S,D] tensor is dense)
+            o = be.attend(q8[:, lo:hi], k_all[:, lo:hi], v_all[:, lo:hi], sq[:, lo:hi], sk[:, lo:hi],
+                          None if v16 else sv[:, lo:hi], sm_scale, p_mode, q.dtype, out=dst, return_lse=False)
+            if dst is None:
+                out[:, lo:hi].copy_(o)
+        return out
+
+    # strategy "ring": K and V share one byte buffer so a ring step is one send and one receive
+    q8, k8 = be.quantize([q, k], [sq, sk])
+    v_send = v.contiguous() if v16 else be.quantize([v], [sv])[0]
+    nk, nv = k8.numel(), v_send.numel() * v_send.element_size()
+    kv = [torch.empty((nk + nv,), dtype=torch.uint8, device=q.device) for _ in range(2)]
+    kv[0][:nk].copy_(k8.view(torch.uint8).reshape(-1))
+    kv[0][nk:].copy_(v_send.view(torch.uint8).reshape(-1))
+    o_acc = torch.empty((B, H, S, D), dtype=torch.float32, device=q.device)
+    lse_acc = torch.empty((B, H, S), dtype=torch.float32, device=q.device)
     cur = 0
     for step in range(world):
         last = step == world - 1
         # 3. start moving the block we hold to the next rank, then compute on it (the transfer only reads it)
         reqs = _ring_exchange(kv[cur], kv[cur ^ 1], group) if not last else []
-        k_blk = kv[cur][0].view(torch.float8_e4m3fn)
-        v_blk = kv[cur][1].view(torch.float8_e4m3fn)
+        k_blk = kv[cur][:nk].view(torch.float8_e4m3fn).view(k8.shape)
+        v_blk = kv[cur][nk:].view(v_send.dtype).view(v_send.shape)
         o_new, lse_new = be.attend(q8, k_blk, v_blk, sq, sk, sv, sm_scale, p_mode, q.dtype)
         # 4. fold the partial result in; the last step writes the 16-bit output directly
         be.merge(o_acc, lse_acc, o_new, lse_new, step == 0, out if last else None)
@@ -212,7 +370,7 @@ def ring_fp8_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, sca
     return out
 
 
-# the function predates the all-gather strategy; this is the name that says what it does
+# the function predates the gather strategy; this is the name that says what it does
 sequence_sharded_fp8_attention = ring_fp8_attention
 
 

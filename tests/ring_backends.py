@@ -13,16 +13,33 @@ class OracleBackend:
     def local_scales(self, tensors):
         return [torch.from_numpy(oracle.head_scales(t.float().numpy())) for t in tensors]
 
-    def quantize(self, tensors, scales):
-        return [torch.from_numpy(oracle.quantize_with_scale(t.float().numpy(), s.numpy())).view(torch.float8_e4m3fn)
-                for t, s in zip(tensors, scales)]
+    def quantize(self, tensors, scales, outs=None):
+        res = [torch.from_numpy(oracle.quantize_with_scale(t.float().numpy(), s.numpy())).view(torch.float8_e4m3fn)
+               for t, s in zip(tensors, scales)]
+        if outs is not None:
+            for o, r in zip(outs, res):
+                o.view(torch.uint8).copy_(r.view(torch.uint8))
+            return list(outs)
+        return res
 
-    def attend(self, q8, k8, v8, sq, sk, sv, sm_scale, p_mode, out_dtype):
-        self.calls.append("attend")
-        o, lse = oracle.attention_block_ref(q8.view(torch.uint8).numpy(), k8.view(torch.uint8).numpy(),
-                                            v8.view(torch.uint8).numpy(), sq.numpy(), sk.numpy(), sv.numpy(),
-                                            sm_scale=sm_scale)
-        return o.to(out_dtype), lse.float()
+    def attend(self, q8, k8, v, sq, sk, sv, sm_scale, p_mode, out_dtype, out=None, return_lse=True):
+        """v: e4m3 with head scales sv, or (sv None: the "16bit" mode) the 16-bit tensor itself."""
+        self.calls.append(("attend", tuple(q8.shape), tuple(k8.shape)))
+        if sv is None:
+            v_bytes, sv_np = None, None
+            q = torch.from_numpy(oracle.dequantize(q8.view(torch.uint8).numpy(), sq.numpy())).double()
+            k = torch.from_numpy(oracle.dequantize(k8.view(torch.uint8).numpy(), sk.numpy())).double()
+            s = (q @ k.transpose(-1, -2)) * sm_scale
+            o, lse = torch.softmax(s, dim=-1) @ v.double(), torch.logsumexp(s, dim=-1)
+        else:
+            o, lse = oracle.attention_block_ref(q8.view(torch.uint8).numpy(), k8.view(torch.uint8).numpy(),
+                                                v.view(torch.uint8).numpy(), sq.numpy(), sk.numpy(), sv.numpy(),
+                                                sm_scale=sm_scale)
+        o = o.to(out_dtype)
+        if out is not None:
+            out.copy_(o)
+            o = out
+        return (o, lse.float()) if return_lse else o
 
     def merge(self, o_acc, lse_acc, o_new, lse_new, first, out=None):
         self.calls.append("merge_first" if first else "merge")

@@ -20,7 +20,9 @@ from conftest import bf16_from_bits
 pytestmark = pytest.mark.gpu
 
 PV = {"fp8": _native.QA_P_E4M3, "fp8_hilo": _native.QA_P_E4M3_HILO, "16bit": _native.QA_P_16BIT}
-ROW_BOUND = {"fp8": 0.30, "fp8_hilo": 0.03, "16bit": 0.03}
+# max-abs error over the row RMS.  The north star's 2e-2 is asserted for the modes whose arithmetic can meet it; a single
+# e4m3 P ("fp8", opt-in) carries 2^-4 relative steps per probability and is only held to a loose sanity bound.
+ROW_BOUND = {"fp8": 0.30, "fp8_hilo": 0.02, "16bit": 0.02}
 
 
 def run_native(q, k, v, *, causal, pv, mode="head-wise", scale=None, return_lse=False):
@@ -89,7 +91,7 @@ def test_golden_fixtures_from_reference(golden_dir, name, pv):
     assert m["cos_sim"] >= 0.999 and m["rmse"] < 1e-2, m
     if pv == "16bit":  # same arithmetic as the reference kernel: agreement at bf16 resolution vs the fp32 statement
         m2 = oracle.compare(out, g["out_ref_fp32"])
-        assert m2["max_abs_over_row_rms"] < 0.03, m2
+        assert m2["max_abs_over_row_rms"] <= 0.02, m2
 
 
 def test_golden_token_wise(golden_dir):
@@ -101,7 +103,7 @@ def test_golden_token_wise(golden_dir):
     out = _native.fp8_attn_fwd(q8, k8, v, sq, sk, None, scale_mode=_native.QA_SCALE_TOKEN, is_causal=False,
                                sm_scale=1.0 / math.sqrt(128), p_mode=PV["16bit"], out_dtype=torch.bfloat16)
     m = oracle.compare(out.float().cpu().numpy(), g["out_ref_fp32"])
-    assert m["cos_sim"] >= 0.9999 and m["max_abs_over_row_rms"] < 0.03, m
+    assert m["cos_sim"] >= 0.9999 and m["max_abs_over_row_rms"] <= 0.02, m
 
 
 # C1 of BASELINE.json plus the reference's own test sweep shapes (tests/test_interface.py:62-84), scaled to H=2
@@ -216,8 +218,9 @@ def test_prequantized_inputs_and_errors():
 
 
 @pytest.mark.parametrize("name", ["C2_flux", "C3_llama"])
-def test_full_size_properties(name):
-    """BASELINE configs at full size: the oracle only scores a slice of rows (it would take minutes otherwise);
+def test_full_size_properties_and_oracle_on_2_heads_x_384_rows(name):
+    """BASELINE configs at full size: the oracle only scores a slice - 2 heads x 384 rows (first / middle / last
+    128), all keys - since it would take minutes otherwise;
     the rest is covered by size-independent properties: rows of softmax sum to one (V = 1 -> O = 1), and
     permuting the keys/values of a non-causal problem leaves O unchanged."""
     B, H, S, D, causal = oracle.CONFIGS[name]
@@ -257,23 +260,30 @@ def test_full_size_properties(name):
         assert m["cos_sim"] >= 0.999 and m["max_abs_over_row_rms"] <= ROW_BOUND[pv], (pv, m)
 
 
-def test_full_size_video_shape_properties():
-    """C4 (B1 H24 S75600 D128, ragged: 75600 = 590 * 128 + 80) on one GPU at full size: finite output, rows of softmax
-    sum to one, and the fp64 oracle on a slice (first / middle / last rows of the first and last head)."""
+@pytest.mark.parametrize("pv", ["16bit", "fp8_hilo", "fp8"])
+def test_full_size_video_shape_oracle_on_2_heads_x_384_rows(pv):
+    """C4 (B1 H24 S75600 D128, ragged: 75600 = 590 * 128 + 80) on one GPU at full size, each P mode against ITS oracle
+    (16-bit V for "16bit", dequantised e4m3 V for the FP8 modes) with its own bound: finite output, rows of softmax
+    sum to one, and the fp64 oracle on a slice (first / middle / last 128 rows of the first and last head, all keys)."""
     B, H, S, D, causal = oracle.CONFIGS["C4_video"]
     g = torch.Generator(device="cuda").manual_seed(4)
     qc, kc, vc = (torch.randn((B, H, S, D), device="cuda", dtype=torch.bfloat16, generator=g) for _ in range(3))
-    out = quantum_attn.fp8_attn_func(qc, kc, vc, is_causal=causal)
-    assert out.shape == qc.shape and bool(torch.isfinite(out).all())
-    ones = quantum_attn.fp8_attn_func(qc, kc, torch.ones_like(vc), is_causal=causal)
-    assert (ones.float() - 1.0).abs().max().item() < 0.01
-    del ones
-    (q8, k8, v8), (sq, sk, sv) = _native.quantize_fp8([qc, kc, vc], _native.QA_SCALE_HEAD)
+    with quantum_attn.config.patch({"attention.pv_mode": pv}):
+        out = quantum_attn.fp8_attn_func(qc, kc, vc, is_causal=causal)
+        assert out.shape == qc.shape and bool(torch.isfinite(out).all())
+        ones = quantum_attn.fp8_attn_func(qc, kc, torch.ones_like(vc), is_causal=causal)
+        assert (ones.float() - 1.0).abs().max().item() < 0.01
+        del ones
     heads = [0, H - 1]
     rows = torch.cat([torch.arange(0, 128), torch.arange(S // 2 - 64, S // 2 + 64), torch.arange(S - 128, S)])
-    deq = lambda x8, sc: torch.from_numpy(oracle.dequantize(x8[:, heads].view(torch.uint8).cpu().numpy(),
-                                                            sc[:, heads].cpu().numpy())).double()
-    qh, kh, vh = deq(q8, sq)[:, :, rows], deq(k8, sk), deq(v8, sv)
+    (q8, k8), (sq, sk) = _native.quantize_fp8([qc[:, heads], kc[:, heads]], _native.QA_SCALE_HEAD)
+    deq = lambda x8, sc: torch.from_numpy(oracle.dequantize(x8.view(torch.uint8).cpu().numpy(), sc.cpu().numpy())).double()
+    qh, kh = deq(q8, sq)[:, :, rows], deq(k8, sk)
+    if pv == "16bit":
+        vh = vc[:, heads].double().cpu()
+    else:
+        (v8,), (sv,) = _native.quantize_fp8([vc[:, heads]], _native.QA_SCALE_HEAD)
+        vh = deq(v8, sv)
     ref = torch.softmax((qh @ kh.transpose(-1, -2)) / math.sqrt(D), -1) @ vh
     m = oracle.compare(out[:, heads][:, :, rows.cuda()].float().cpu().numpy(), ref.numpy())
-    assert m["cos_sim"] >= 0.999 and m["max_abs_over_row_rms"] <= ROW_BOUND["fp8"], m
+    assert m["cos_sim"] >= 0.999 and m["max_abs_over_row_rms"] <= ROW_BOUND[pv], (pv, m)

@@ -53,22 +53,29 @@ def _ring_worker(rank, world, port, S_local, tmp):
         # make the shards' amax differ so that the MAX all-reduce matters
         k = k * torch.linspace(0.5, 2.0, S_local * world).view(1, 1, -1, 1).to(k.dtype)
         sl = slice(rank * S_local, (rank + 1) * S_local)
-        be = OracleBackend()
-        out = parallel.ring_fp8_attention(q[:, :, sl].contiguous(), k[:, :, sl].contiguous(),
-                                          v[:, :, sl].contiguous(), backend=be, strategy="ring")
-        assert be.calls == ["attend", "merge_first"] + ["attend", "merge"] * (world - 1)
-        # the all-gather layout: two launches whatever the world size, same quantised bytes
-        be2 = OracleBackend()
-        out_g = parallel.ring_fp8_attention(q[:, :, sl].contiguous(), k[:, :, sl].contiguous(),
-                                            v[:, :, sl].contiguous(), backend=be2, strategy="gather")
-        assert be2.calls == ["attend", "merge_first", "attend", "merge"]
-        assert torch.allclose(out_g.float(), out.float(), atol=2e-2, rtol=2e-2)
+        res = {}
+        loc = [t[:, :, sl].contiguous() for t in (q, k, v)]
+        for pv in ("fp8", "16bit"):
+            be = OracleBackend()
+            out = parallel.ring_fp8_attention(*loc, backend=be, strategy="ring", pv_mode=pv)
+            assert [c[0] if isinstance(c, tuple) else c for c in be.calls] == \
+                ["attend", "merge_first"] + ["attend", "merge"] * (world - 1)
+            # the gather strategy: per head group ONE launch over all keys, no merge; same quantised bytes
+            be2 = OracleBackend()
+            out_g = parallel.ring_fp8_attention(*loc, backend=be2, strategy="gather", pv_mode=pv, head_groups=2)
+            assert be2.calls == [("attend", (B, 1, S_local, D), (B, 1, S_local * world, D))] * H
+            assert torch.allclose(out_g.float(), out.float(), atol=2e-2, rtol=2e-2)
+            be3 = OracleBackend()
+            out_1 = parallel.ring_fp8_attention(*loc, backend=be3, strategy="gather", pv_mode=pv)
+            assert len(be3.calls) == 1 and torch.equal(out_1, out_g)  # (tiny problem: one group of all heads)
+            res[pv] = (out, out_g)
         assert parallel.default_seq_strategy() in parallel.SEQ_STRATEGIES
+        assert parallel.default_seq_transport() in parallel.SEQ_TRANSPORTS
         # head-sharded layout on the same data: rank r computes its heads with a stand-in kernel, gather returns all
         def fake_attn(q_, k_, v_):
             return (q_.float() + k_.float().mean(2, keepdim=True) + v_.float().mean(2, keepdim=True)).to(q_.dtype)
         full = parallel.head_sharded_fp8_attention(q, k, v, gather=(H % world == 0), _attn=fake_attn)
-        torch.save({"out": out, "out_gather": out_g, "heads": full}, os.path.join(tmp, f"r{rank}.pt"))
+        torch.save({"res": res, "heads": full}, os.path.join(tmp, f"r{rank}.pt"))
     finally:
         dist.destroy_process_group()
 
@@ -85,12 +92,14 @@ def test_ring_matches_unsharded_oracle(world, tmp_path):
     q8, sq = oracle.quantize_fp8(q.float().numpy(), "head-wise")
     k8, sk = oracle.quantize_fp8(k.float().numpy(), "head-wise")
     v8, sv = oracle.quantize_fp8(v.float().numpy(), "head-wise")
-    ref = oracle.fp8_attention_ref(q8, k8, v8, sq, sk, scale_v=sv)
-    for key in ("out", "out_gather"):
-        got = torch.cat([torch.load(os.path.join(tmp_path, f"r{r}.pt"))[key] for r in range(world)], dim=2)
-        m = oracle.compare(got.float().numpy(), ref.numpy())
-        # bf16 partial results and a bf16 output: two roundings of 2^-9
-        assert m["finite"] and m["cos_sim"] > 0.99999 and m["max_abs_over_row_rms"] < 2e-2, (key, m)
+    refs = {"fp8": oracle.fp8_attention_ref(q8, k8, v8, sq, sk, scale_v=sv),
+            "16bit": oracle.fp8_attention_ref(q8, k8, v.float().numpy(), sq, sk)}  # the reference's op: 16-bit V
+    for pv, ref in refs.items():
+        for i, key in enumerate(("ring", "gather")):
+            got = torch.cat([torch.load(os.path.join(tmp_path, f"r{r}.pt"))["res"][pv][i] for r in range(world)], dim=2)
+            m = oracle.compare(got.float().numpy(), ref.numpy())
+            # bf16 partial results and a bf16 output: two roundings of 2^-9
+            assert m["finite"] and m["cos_sim"] > 0.99999 and m["max_abs_over_row_rms"] < 2e-2, (pv, key, m)
     if H % world == 0:
         heads = [torch.load(os.path.join(tmp_path, f"r{r}.pt"))["heads"] for r in range(world)]
         want = (q.float() + k.float().mean(2, keepdim=True) + v.float().mean(2, keepdim=True)).to(q.dtype)
@@ -124,15 +133,17 @@ def test_merge_ref_is_exact_split_softmax():
     assert torch.equal(o2, oa) and torch.equal(l2, la)
 
 
-@pytest.mark.parametrize("world,rank", [(2, 0), (2, 1), (4, 2), (8, 0), (8, 7)])
-def test_concat_other_blocks_layout(world, rank):
-    """[world,2,B,H,S,D] gathered bytes -> per head, the blocks of every other rank end to end in rank order."""
-    B, H, S, D = 1, 3, 5, 64
-    g = torch.Generator().manual_seed(world * 10 + rank)
-    kv_all = torch.randint(0, 256, (world, 2, B, H, S, D), dtype=torch.uint8, generator=g)
-    got = parallel._concat_other_blocks(kv_all, rank)
-    want = torch.cat([kv_all[r] for r in range(world) if r != rank], dim=3)
-    assert got.shape == (2, B, H, (world - 1) * S, D) and torch.equal(got, want)
+def test_head_chunks_fill_whole_waves():
+    """Head groups of the gather strategy: contiguous, cover every head once, and sized so a launch fills the SMs in
+    whole waves where the shape allows it (C4 over 8 / 4 / 2 ranks: 37 / 74 / 148 CTAs per head on 148 SMs)."""
+    for world, want_hc in ((8, 4), (4, 2), (2, 2)):
+        ch = parallel.head_chunks(1, 24, 75600 // world)
+        assert ch[0] == (0, want_hc) and ch[-1][1] == 24
+        assert all(a[1] == b[0] for a, b in zip(ch, ch[1:])) and len(ch) <= 12
+        ctas = (ch[0][1] - ch[0][0]) * -(-(75600 // world) // 256)
+        assert ctas % 148 == 0
+    assert parallel.head_chunks(2, 3, 100) == [(0, 3)]
+    assert parallel.head_chunks(1, 1, 10 ** 6) == [(0, 1)]
 
 
 def test_unknown_sequence_strategy_is_rejected(monkeypatch):
