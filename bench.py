@@ -101,7 +101,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.01)
+            time.sleep(0.002)
 
     def stop(self):
         self._stop_evt.set()
@@ -208,6 +208,293 @@ def accuracy_vs_sdpa(q, k, v, causal, out, heads=(0, -1), v_16bit=False):
                        " (torch on the GPU, untimed)"}
 
 
+def _slice_accuracy(out_rows, q8, k8, sq, sk, vd, rows, heads, D):
+    """cos-sim / max-abs-over-row-RMS of `out_rows` [1,len(heads),len(rows),D] against fp64 softmax(QK^T/sqrt(D))V on the
+    dequantised e4m3 Q / K and the value tensor `vd` (already dequantised or 16-bit), for the chosen heads and rows."""
+    cos, mx = [], []
+    for i, h in enumerate(heads):
+        qd = q8[0, h][rows].double() * sq[0, h].double()
+        kd = k8[0, h].double() * sk[0, h].double()
+        ref = torch.softmax((qd @ kd.T) / math.sqrt(D), dim=-1) @ vd[i]
+        got = out_rows[0, i].double()
+        cos.append(float((got * ref).sum() / (got.norm() * ref.norm())))
+        mx.append(float(((got - ref).abs() / ref.pow(2).mean(dim=-1, keepdim=True).sqrt()).max()))
+    return {"cos_sim": min(cos), "max_abs_over_row_rms": max(mx)}
+
+
+def seq_sharded_block(dev, rank, world, dist, steps, warmup):
+    """BASELINE.json config 4 as ONE problem over all ranks (strong scaling): the long-video shape B1 H24 S75600 D128,
+    sequence-sharded (quantumattention_b200/parallel.py).  Returns (on rank 0) the block that goes on the bench line:
+    ms/step (max over ranks), TFLOP/s, strong-scaling efficiency against the same call on ONE GPU measured in this run,
+    the transfer's bytes and achieved GB/s, a time split from CUDA events, and the accuracy of every P mode against the
+    fp64 oracle on a slice (rank 0's first / middle / last 64 rows of two heads, all 75 600 keys)."""
+    import quantum_attn
+    from quantumattention_b200 import _native, parallel
+
+    B, H, S, D, _ = WORKLOADS["C4_video"]
+    if S % world:
+        return {"skipped": f"S={S} does not split over {world} ranks"}
+    S_loc = S // world
+    pv_mode = parallel.seq_pv_mode()
+    strategy, transport = parallel.default_seq_strategy(), parallel.default_seq_transport()
+
+    def full_qkv():
+        g = torch.Generator(device=dev).manual_seed(4321)  # same device type + seed on every rank: same sequence
+        return [torch.randn((B, H, S, D), device=dev, dtype=torch.bfloat16, generator=g) for _ in range(3)]
+
+    full = full_qkv()
+    loc = [t[:, :, rank * S_loc:(rank + 1) * S_loc].contiguous() for t in full]
+    del full
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    transport_error = None
+    try:
+        for _ in range(max(2, warmup // 4)):
+            out = parallel.ring_fp8_attention(*loc)
+        barrier()
+    except Exception as e:  # e.g. peer transport unavailable on this box: fall back to NCCL and say so
+        if transport == "nccl":
+            raise
+        transport_error = repr(e)[:200]
+        os.environ["QA_SEQ_TRANSPORT"] = transport = "nccl"
+        for _ in range(max(2, warmup // 4)):
+            out = parallel.ring_fp8_attention(*loc)
+        barrier()
+    n = max(5, min(steps, 30))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = _native.launch_total
+    barrier()
+    e0.record()
+    for _ in range(n):
+        out = parallel.ring_fp8_attention(*loc)
+    e1.record()
+    barrier()
+    launches = (_native.launch_total - l0) // n
+    t = torch.tensor([e0.elapsed_time(e1) / n], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+
+    # time split (separate untimed pass: the marks are CUDA events on the calling stream at the phase boundaries)
+    split = None
+    if strategy == "gather":
+        acc = {}
+        reps = 5
+        for _ in range(reps):
+            parallel.trace_marks = []
+            parallel.ring_fp8_attention(*loc)
+            torch.cuda.synchronize()
+            marks, parallel.trace_marks = parallel.trace_marks, None
+            for (_, a), (lb, b) in zip(marks, marks[1:]):
+                acc[lb] = acc.get(lb, 0.0) + a.elapsed_time(b)
+        split = {("transfer_exposed" if k_ == "wait" else ("attention" if k_ == "attend" else k_)) + "_ms": v_ / reps
+                 for k_, v_ in acc.items()}
+        split["note"] = ("scales = amax pass + all_reduce(MAX); quant_kv / quant_q = quantise with the global scales (K/V "
+                         "first: they travel); transfer_exposed = time the compute stream waited for blocks; attention = "
+                         "the per-head-group launches")
+
+    # the transfer alone: every head group's blocks, nothing else running
+    v_item = 2 if pv_mode == "16bit" else 1
+    wire_bytes = (world - 1) * B * H * S_loc * D * (1 + v_item)  # received per rank per step
+    k_loc = torch.empty((B, H, S_loc, D), dtype=torch.uint8, device=dev)
+    v_loc = torch.empty((B, H, S_loc, D * v_item), dtype=torch.uint8, device=dev)
+    k_all = torch.empty((B, H, S, D), dtype=torch.uint8, device=dev)
+    v_all = torch.empty((B, H, S, D * v_item), dtype=torch.uint8, device=dev)
+    chunks = parallel.head_chunks(B, H, S_loc)
+    gather_ms = None
+    try:
+        for rep in range(4):
+            barrier()
+            if rep == 1:
+                e0.record()
+            for lo, hi in chunks:
+                parallel._nccl_gather_heads([k_loc, v_loc], [k_all, v_all], lo, hi, None).wait()
+        e1.record()
+        barrier()
+        tg = torch.tensor([e0.elapsed_time(e1) / 3], device=dev, dtype=torch.float64)
+        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        gather_ms = float(tg.item())
+    except Exception as e:
+        gather_ms = None
+        transport_error = (transport_error or "") + " gather probe: " + repr(e)[:120]
+    del k_loc, v_loc, k_all, v_all
+
+    # accuracy of every P mode on a slice, and the same call on one GPU (rank 0 only; the others wait at the barrier)
+    accuracy, one_gpu_ms = {}, None
+    heads = [0, H - 1]
+    rows = torch.cat([torch.arange(0, 64), torch.arange(S_loc // 2 - 32, S_loc // 2 + 32),
+                      torch.arange(S_loc - 64, S_loc)]).to(dev)
+    outs = {}
+    for mode in ("16bit", "fp8_hilo", "fp8"):
+        o = parallel.ring_fp8_attention(*loc, pv_mode=mode)
+        outs[mode] = o[:, heads][:, :, rows].clone()
+        del o
+    barrier()
+    if rank == 0:
+        full = full_qkv()
+        try:
+            (q8, k8, v8), (sq, sk, sv) = _native.quantize_fp8([t[:, heads].contiguous() for t in full],
+                                                              _native.QA_SCALE_HEAD)
+            v16 = [full[2][0, h].double() for h in heads]
+            vdq = [v8[0, i].double() * sv[0, i].double() for i in range(len(heads))]
+            hs = list(range(len(heads)))
+            for mode in ("16bit", "fp8_hilo", "fp8"):
+                accuracy[mode] = _slice_accuracy(outs[mode], q8, k8, sq, sk, v16 if mode == "16bit" else vdq, rows,
+                                                 hs, D)
+            del q8, k8, v8, v16, vdq
+        except Exception as e:
+            accuracy = {"error": repr(e)[:200]}
+        try:
+            with quantum_attn.config.patch({"attention.pv_mode": pv_mode}):
+                for i in range(3):
+                    if i == 1:
+                        e0.record()
+                    quantum_attn.fp8_attn_func(*full)
+                e1.record()
+                torch.cuda.synchronize()
+            one_gpu_ms = e0.elapsed_time(e1) / 2
+        except Exception as e:
+            one_gpu_ms = None
+        del full
+    barrier()
+    if rank != 0:
+        return None
+    fl = flops_of(B, H, S, D, False)
+    return {
+        "workload": f"C4_video: ONE problem B={B} H={H} S={S} D={D} non-causal over {world} GPUs ({S_loc} tokens per rank)",
+        "scaling": "strong", "n_gpus": world, "ms_per_step": ms, "steps": n, "value": fl / (ms * 1e-3) / 1e12, "unit": UNIT,
+        "per_gpu_tflops": fl / (ms * 1e-3) / 1e12 / world, "pv_mode": pv_mode, "strategy": strategy,
+        "transport": transport, "transport_error": transport_error, "head_groups": len(chunks),
+        "gpu_launches_per_step": launches,
+        "one_gpu_ms_same_run": one_gpu_ms,
+        "strong_scaling_efficiency": (one_gpu_ms / (world * ms)) if one_gpu_ms else None,
+        "wire": {"bytes_received_per_rank_per_step": wire_bytes,
+                 "what": "e4m3 K + " + ("16-bit V" if v_item == 2 else "e4m3 V") + " blocks of the other ranks",
+                 "gather_alone_ms": gather_ms,
+                 "gather_alone_gbs": (wire_bytes / (gather_ms * 1e-3) / 1e9) if gather_ms else None,
+                 "gather_alone_how": "grouped NCCL all-gathers of every head group back to back, nothing else running, "
+                                     "max over ranks (measured reference on this pool: 770 GB/s peer copy per direction)"},
+        "time_split": split,
+        "accuracy": accuracy,
+        "accuracy_against": "fp64 softmax(QK^T)V on the dequantised e4m3 Q, K and the mode's V (16-bit for '16bit', "
+                            "dequantised e4m3 otherwise); rank 0's first / middle / last 64 rows of heads 0 and 23, all "
+                            "75600 keys; bounds: cos >= 0.999, max-abs <= 2e-2 of the row RMS ('16bit', 'fp8_hilo')",
+    }
+
+
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this rank's threads to the CPUs of its GPU's NUMA node and prefer that node for new pages (the pinned
+    staging buffers of the end-to-end leg), so host<->device copies do not cross the socket interconnect.  Best
+    effort: reports what it could do.  (Round 1: all eight ranks ran on node 0 with buffers from one node and the
+    end-to-end figure scaled 1.0 / 0.79 / 0.41 / 0.29 over 1 / 2 / 4 / 8 GPUs.)"""
+    info = {"gpu_numa_node": None, "cpus_bound": None, "mempolicy": None}
+    try:
+        p = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        info["gpu_numa_node"] = node
+        if node < 0:
+            return info
+        cpus = set()
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if use:
+            os.sched_setaffinity(0, use)
+            info["cpus_bound"] = f"{len(use)} CPUs of node {node}"
+        else:
+            info["cpus_bound"] = f"none of node {node}'s CPUs is in this process's cpuset ({len(allowed)} allowed)"
+        import ctypes
+        libc = ctypes.CDLL("libc.so.6", use_errno=True)
+        mask = ctypes.c_ulong(1 << node)
+        rc = libc.syscall(238, 1, ctypes.byref(mask), 64)  # set_mempolicy(MPOL_PREFERRED, {node})
+        info["mempolicy"] = f"preferred node {node}" if rc == 0 else f"set_mempolicy failed (errno {ctypes.get_errno()})"
+    except Exception as e:
+        info["error"] = repr(e)[:160]
+    return info
+
+
+def external_bars(sets, causal, fl, dev):
+    """On-box comparators, rank 0, untimed extras: none of these is the reference, and none
+    computes the reference's FP8 function - they are the bf16 / fp16 attention kernels of the stock libraries on the
+    same shape, for scale.  Kernel-only, CUDA events, 10 launches after 3 warm-ups, rotating inputs."""
+    import torch.nn.functional as F
+    from torch.nn.attention import SDPBackend, sdpa_kernel
+
+    res = {}
+
+    def timeit(fn):
+        for i in range(3):
+            fn(*sets[i % len(sets)])
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(10):
+            fn(*sets[i % len(sets)])
+        b.record()
+        torch.cuda.synchronize()
+        return fl / (a.elapsed_time(b) / 10 * 1e-3) / 1e12
+
+    for name, backend in (("torch_sdpa_cudnn_bf16", SDPBackend.CUDNN_ATTENTION), ("torch_sdpa_flash_bf16", SDPBackend.FLASH_ATTENTION)):
+        try:
+            def fn(q, k, v, _b=backend):
+                with sdpa_kernel(_b):
+                    return F.scaled_dot_product_attention(q, k, v, is_causal=causal)
+            res[name] = timeit(fn)
+        except Exception as e:
+            res[name] = "unavailable: " + repr(e)[:100]
+    try:
+        from flash_attn import flash_attn_func
+
+        bshd = [tuple(t.transpose(1, 2).contiguous() for t in s_) for s_ in sets[:2]]
+
+        def fa(q, k, v):
+            return flash_attn_func(q, k, v, causal=causal)
+        for i in range(3):
+            fa(*bshd[i % 2])
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(10):
+            fa(*bshd[i % 2])
+        b.record()
+        torch.cuda.synchronize()
+        res["flash_attn_2_bf16"] = fl / (a.elapsed_time(b) / 10 * 1e-3) / 1e12
+        del bshd
+    except Exception as e:
+        res["flash_attn_2_bf16"] = "unavailable: " + repr(e)[:100]
+    try:
+        import flashinfer
+
+        bshd = [tuple(t[0].transpose(0, 1).contiguous() for t in s_) for s_ in sets[:2]]  # [S, H, D]
+
+        def fi(q, k, v):
+            return flashinfer.single_prefill_with_kv_cache(q, k, v, causal=causal)
+        for i in range(3):
+            fi(*bshd[i % 2])
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(10):
+            fi(*bshd[i % 2])
+        b.record()
+        torch.cuda.synchronize()
+        res["flashinfer_single_prefill_bf16"] = fl / (a.elapsed_time(b) / 10 * 1e-3) / 1e12
+        del bshd
+    except Exception as e:
+        res["flashinfer_single_prefill_bf16"] = "unavailable: " + repr(e)[:100]
+    res["unit"] = UNIT
+    res["note"] = ("stock bf16 attention kernels on the same shape and FLOP count (kernel only); the CuTe-DSL Blackwell FMHA "
+                   "with Float8E4M3FN inputs is measured by scripts/cutedsl_fmha_bar.sh when its JIT works offline")
+    return res
+
+
 def main():
     out = _claim_stdout()
     ap = argparse.ArgumentParser()
@@ -216,9 +503,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2_flux", choices=sorted(WORKLOADS))
-    ap.add_argument("--event-every", type=int, default=8,
+    ap.add_argument("--event-every", type=int, default=None,
                     help="bracket the attention kernel with CUDA events on every N-th timed step (the two event records "
-                         "cost about 6 us of GPU time per bracketed step on C2; 1 = every step)")
+                         "cost about 6 us of GPU time per bracketed step on C2; 1 = every step; default 8, or 4 for "
+                         "runs of fewer than 100 steps so that a short run still has several samples)")
+    ap.add_argument("--no-seq-sharded", action="store_true",
+                    help="N > 1: skip the C4 strong-scaling block (one sequence sharded over all ranks)")
+    ap.add_argument("--no-comparators", action="store_true", help="skip the stock-library attention kernels")
     ap.add_argument("--pv-mode", default=None, choices=["fp8", "fp8_hilo", "16bit"])
     ap.add_argument("--e2e-steps", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -232,25 +523,37 @@ def main():
     ring = args.workload == "C4_video" and world > 1
     if args.steps is None:
         args.steps = 1000 if S <= 16384 else 30
+    if args.event_every is None:
+        args.event_every = 8 if args.steps >= 100 else 4
     if S > 16384:
         args.e2e_steps = min(args.e2e_steps, 10)
+    # (everything in `config` is a function of the command line and the environment alone, so the reference arm of
+    # the same command prints the same dict)
+    pv_mode = args.pv_mode or os.getenv("QUANTUM_ATTN_PV_MODE", "16bit")
+    bytes_per_set = 3 * B * H * (S // world if ring else S) * D * 2
+    n_sets = max(2, math.ceil(300e6 / bytes_per_set))
     config = {
         "workload": f"{args.workload}: B={B} (per GPU) H={H} S={S} D={D} causal={causal}, head-wise FP8 scales",
         "per_gpu_batch": B, "heads": H, "seq_len": S, "head_dim": D, "causal": causal,
         "parallelism": f"batch x head sharding over {world} GPU(s), no collective",
+        "l2_policy": f"rotating {n_sets} input sets ({n_sets * bytes_per_set / 1e6:.0f} MB > 126 MB L2)",
+        "kernel_timing": (f"CUDA events around the attention launch of every {args.event_every}-th timed step, on its "
+                          "stream (roofline.achieved is their mean)"),
+        "pv_mode": pv_mode,
     }
     if ring:
         if S % world:
             raise SystemExit(f"bench.py: S={S} does not split over {world} ranks")
         config["workload"] = (f"{args.workload}: ONE problem B={B} H={H} S={S} D={D} causal={causal} over {world} GPUs, "
                               f"{S // world} tokens per rank, head-wise FP8 scales (global via all_reduce MAX)")
-        from quantumattention_b200.parallel import default_seq_strategy
+        from quantumattention_b200.parallel import default_seq_strategy, default_seq_transport
         config["parallelism"] = (
-            f"sequence sharding over {world} GPUs: e4m3 K/V blocks by NCCL send/recv ring, (O, LSE) merge per block"
+            f"sequence sharding over {world} GPUs: e4m3 K (+ V) blocks by NCCL send/recv ring, (O, LSE) merge per block"
             if default_seq_strategy() == "ring" else
-            f"sequence sharding over {world} GPUs: one NCCL all-gather of the e4m3 K/V blocks under the local block's "
-            f"attention, one launch over the other ranks' keys, one (O, LSE) merge")
+            f"sequence sharding over {world} GPUs: every rank's K / V blocks gathered per head group into the kernel's "
+            f"layout ({default_seq_transport()} transport), one launch per head group over all keys, no merge")
         config["seq_strategy"] = default_seq_strategy()
+        config["seq_transport"] = default_seq_transport()
 
     # ------------------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
@@ -282,17 +585,11 @@ def main():
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=dev)
-    if args.pv_mode:
-        quantum_attn.config.attention.pv_mode = args.pv_mode
-    pv_mode = quantum_attn.config.attention.pv_mode
-    if ring:  # e4m3 K/V on the wire: the sequence-sharded path has no 16-bit-V mode (parallel.seq_pv_mode)
-        from quantumattention_b200.parallel import seq_pv_mode
-        pv_mode = seq_pv_mode()
+    quantum_attn.config.attention.pv_mode = pv_mode
     _native.load(build_if_missing=False)
+    host_binding = bind_to_gpu_numa_node(local_rank)
 
     # rotating input sets so the working set (> 126 MB L2) is not L2-resident between steps
-    bytes_per_set = 3 * B * H * (S // world if ring else S) * D * 2
-    n_sets = max(2, math.ceil(300e6 / bytes_per_set))
 
     def make_qkv(seed):  # CPU-generated randn so every run (and the CPU arm) sees the same bits
         g = torch.Generator(device="cpu").manual_seed(seed)
@@ -306,10 +603,6 @@ def main():
         else:
             q, k, v = make_qkv(1000 * rank + i)
         sets.append((q.to(dev), k.to(dev), v.to(dev)))
-    config["l2_policy"] = f"rotating {n_sets} input sets ({n_sets * bytes_per_set / 1e6:.0f} MB > 126 MB L2)"
-    config["kernel_timing"] = (f"CUDA events around the attention launch of every {args.event_every}-th timed step, on its "
-                               "stream (roofline.achieved is their mean)")
-    config["pv_mode"] = pv_mode
 
     from quantumattention_b200 import parallel
 
@@ -414,6 +707,29 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
     e2e_value = job_fl / (e2e_ms / args.e2e_steps * 1e-3) / 1e12
+    # host link per rank, all ranks copying at once (what bounds the end-to-end figure): one direction at a time
+    link = {}
+    for name, dst_, src_, strm in (("h2d_gbs", dbuf[0][0], hq, s_in), ("d2h_gbs", houts[0], dbuf[0][0], s_out)):
+        barrier()
+        a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(strm):
+            a_.record(strm)
+            for _ in range(8):
+                dst_.copy_(src_, non_blocking=True)
+            b_.record(strm)
+        barrier()
+        link[name] = 8 * hq.numel() * hq.element_size() / (a_.elapsed_time(b_) * 1e-3) / 1e9
+    if dist is not None:
+        lt = torch.tensor([link["h2d_gbs"], link["d2h_gbs"]], device=dev, dtype=torch.float64)
+        allv = [torch.empty_like(lt) for _ in range(world)]
+        dist.all_gather(allv, lt)
+        link = {"h2d_gbs_per_rank": [round(float(x[0]), 1) for x in allv],
+                "d2h_gbs_per_rank": [round(float(x[1]), 1) for x in allv]}
+    link["how"] = "8 back-to-back copies of one pinned [B,H,S,D] bf16 tensor per direction, every rank at the same time"
+    bindings = [host_binding]
+    if dist is not None:
+        bindings = [None] * world
+        dist.all_gather_object(bindings, host_binding)
 
     # ---- the quantiser alone (HBM-bound leg of the step): Q, K, V of one input set per launch, rotating sets
     quant_ms = None
@@ -423,12 +739,15 @@ def main():
         for i in range(3):
             _native.quantize_fp8(list(sets[i % n_sets])[:nq], qmode)
         torch.cuda.synchronize()
-        _native.quant_events = []
+        # average launch duration over 50 back-to-back launches on rotating sets (one event pair round the lot: a pair
+        # per launch adds ~6 us of event-record time to a ~25 us kernel)
+        qa_, qb_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        qa_.record()
         for i in range(50):
             _native.quantize_fp8(list(sets[i % n_sets])[:nq], qmode)
+        qb_.record()
         torch.cuda.synchronize()
-        qev, _native.quant_events = _native.quant_events, None
-        quant_ms = statistics.mean(a.elapsed_time(b) for a, b in qev)  # memset + kernel, per call, on the stream
+        quant_ms = qa_.elapsed_time(qb_) / 50
         # host-side cost of one step (python + ctypes + allocator), GPU not waited for (not in ring mode: a step
         # there holds collectives and every rank would have to take part)
         host_us = None
@@ -473,6 +792,13 @@ def main():
         ev, _native.attn_events = _native.attn_events, None
         other_modes["attn_func_bf16"] = fl / (statistics.mean(a.elapsed_time(b) for a, b in ev) * 1e-3) / 1e12
 
+    comparators = None
+    if rank == 0 and world == 1 and not args.no_comparators and S <= 16384:
+        try:
+            comparators = external_bars(sets, causal, fl, dev)
+        except Exception as e:
+            comparators = {"error": repr(e)[:200]}
+
     accuracy = None
     if rank == 0 and not ring:
         try:
@@ -485,6 +811,16 @@ def main():
         except Exception as e:  # a reporting extra: never lose the bench line to it
             accuracy = {"error": repr(e)[:200]}
 
+    seq_block = None
+    if world > 1 and not args.no_seq_sharded:
+        del sets, dbuf, hq, hk, hv, houts
+        torch.cuda.empty_cache()
+        try:
+            seq_block = seq_sharded_block(dev, rank, world, dist, args.steps, args.warmup)
+        except Exception as e:  # never lose the main line to the extra block
+            seq_block = {"error": repr(e)[:300]}
+        sets = None
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -492,7 +828,14 @@ def main():
 
     peaks = load_peaks()
     fp8_meas = fp8_gemm_peak(dev)
-    launch_fl = fl // (world * world) if ring else fl  # a ring step attends S/N queries to S/N keys
+    if ring:
+        # launches per step: one per head group over all keys (gather) or one per key block (ring); every launch of a
+        # step does the same share of the rank's FLOPs (fl / world)
+        from quantumattention_b200.parallel import default_seq_strategy, head_chunks
+        n_l = len(head_chunks(B, H, S_loc)) if default_seq_strategy() == "gather" else world
+        launch_fl = fl // world // n_l
+    else:
+        launch_fl = fl
     achieved = launch_fl / (attn_ms * 1e-3) / 1e12
     # The driver measures bf16 only; kind::f8f6f4 runs at exactly twice the bf16 rate on the same datapath, so the
     # FP8 denominator is 2 x the MEASURED bf16 GEMM burst figure.  Spec and measured-FP8-GEMM fractions sit beside it.
@@ -513,6 +856,9 @@ def main():
     roofline = {
         "kernel": "attn_fwd_kernel", "bound": "tensor", "achieved": achieved, "peak": peak, "unit": UNIT,
         "frac": achieved / peak, "traffic": traffic,
+        "traffic_source": "profiles/roofline_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of this kernel "
+                          "from an `ncu --set full` capture of this workload and mode (static, not measured in this run)",
+        "kernel_samples": len(events),
         "peak_source": f"{peak_note} ({peaks['source']} MEASURED_PEAKS.json burst {peaks['bf16_tflops']}); "
                        "the file holds no FP8 figure",
         "frac_of_fp8_spec_4500": achieved / FP8_SPEC_TFLOPS,
@@ -524,7 +870,8 @@ def main():
     n_quant = 2 if pv_mode == "16bit" else 3  # V stays 16-bit in the reference's mode: only Q and K are quantised
     quant_bytes = n_quant * B * H * S_loc * D * 3 + n_quant * B * H * 4  # 2 B in + 1 B out per element, + scales
     quantiser = {
-        "kernel": "quant_head_ring_kernel (+ workspace memset)", "bound": "hbm", "ms": quant_ms,
+        "kernel": "quant_head_ring_kernel", "bound": "hbm", "ms": quant_ms,
+        "how": "mean launch duration over 50 back-to-back launches on rotating input sets, one CUDA-event pair round the lot",
         "achieved": quant_bytes / (quant_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
         "frac": quant_bytes / (quant_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes": quant_bytes,
         "traffic": None,
@@ -549,7 +896,12 @@ def main():
         "other_pv_modes_kernel_tflops": other_modes,
         "other_pv_modes_step_tflops": other_steps,
         "accuracy": accuracy,
+        "comparators": comparators,
+        "host_link": link,
+        "host_binding": bindings,
     }
+    if seq_block is not None:
+        line["seq_sharded"] = seq_block
     if world == 1 and not args.no_cpu_baseline:
         leg = cpu_reference_leg(args.workload)
         line["cpu_baseline"] = {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")}

@@ -101,6 +101,18 @@ def _ring_exchange(send_buf: torch.Tensor, recv_buf: torch.Tensor, group) -> lis
     return dist.batch_isend_irecv(ops_)
 
 
+# bench.py's time split: set to a list to collect (label, CUDA event) marks on the calling stream at the phase
+# boundaries of ring_fp8_attention (gather strategy); None (default) records nothing
+trace_marks = None
+
+
+def _mark(label: str, device) -> None:
+    if trace_marks is not None:
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(torch.cuda.current_stream(device))
+        trace_marks.append((label, ev))
+
+
 SEQ_STRATEGIES = ("gather", "ring")
 SEQ_TRANSPORTS = ("nccl", "peer")
 
@@ -292,11 +304,15 @@ def ring_fp8_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, sca
     sm_scale = (1.0 / math.sqrt(D)) if scale is None else float(scale)
 
     # 1. head scales of the WHOLE sequence: local scales, one MAX all-reduce (scale is monotone in amax)
+    if q.is_cuda:
+        _mark("start", q.device)
     scales = torch.stack(be.local_scales([q, k] if v16 else [q, k, v]))  # [2 or 3, B, H] fp32
     if world > 1:
         dist.all_reduce(scales, op=dist.ReduceOp.MAX, group=group)
     sq, sk, sv = scales[0], scales[1], (None if v16 else scales[2])
     out = torch.empty_like(q)
+    if q.is_cuda:
+        _mark("scales", q.device)
 
     if world == 1:
         q8, k8 = be.quantize([q, k], [sq, sk])
@@ -334,15 +350,23 @@ def ring_fp8_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, sca
             v_all = torch.empty((B, H, world * S, D), dtype=v_send.dtype, device=q.device)
             waits = [_nccl_gather_heads([k8, v_send], [k_all, v_all], lo, hi, group) for lo, hi in chunks]
             wait = lambda w: w.wait()
+        if q.is_cuda:
+            _mark("quant_kv", q.device)
         (q8,) = be.quantize([q], [sq])
+        if q.is_cuda:
+            _mark("quant_q", q.device)
         # 3. one launch per head group over ALL keys, as its blocks land
         for (lo, hi), w in zip(chunks, waits):
             wait(w)
+            if q.is_cuda:
+                _mark("wait", q.device)
             dst = out[:, lo:hi] if B == 1 else None  # (a head range of a [1,H,S,D] tensor is dense)
             o = be.attend(q8[:, lo:hi], k_all[:, lo:hi], v_all[:, lo:hi], sq[:, lo:hi], sk[:, lo:hi],
                           None if v16 else sv[:, lo:hi], sm_scale, p_mode, q.dtype, out=dst, return_lse=False)
             if dst is None:
                 out[:, lo:hi].copy_(o)
+            if q.is_cuda:
+                _mark("attend", q.device)
         return out
 
     # strategy "ring": K and V share one byte buffer so a ring step is one send and one receive
