@@ -100,6 +100,9 @@ constexpr float kLog2e = 1.4426950408889634f;
 #ifndef QA_DECIDEQ
 #define QA_DECIDEQ 1   // quads of exponentials left when the rescale decision for the next step is taken
 #endif
+#ifndef QA_SPLIT
+#define QA_SPLIT 0     // 1: TWO softmax threads per query row (each owns half of a step's 64 columns): 4 softmax warps per scheduler
+#endif
 
 // QK16_: Q and K stay 16-bit (bf16 / fp16) and QK^T runs as kind::f16 - the reference's `attn_func` path
 // (src/quantum_attn/tk/attention.py:238-240,289-313); it implies the 16-bit P mode and has no dequantisation scales.
@@ -116,10 +119,18 @@ struct AttnCfg {
     // in 128-row units.
     static constexpr bool SOLO = (QA_SOLO != 0) && D_ <= 128 && !QK16_ && !(PMODE_ == QA_P_16BIT);
     static constexpr int NQ = (D_ <= 128 && !SOLO) ? 2 : 1;  // O for two tiles does not fit TMEM at D = 256
+    // NH softmax threads share a query row: thread `hf` of a row owns columns [hf * CW, (hf + 1) * CW) of every 64-key
+    // step (TMEM lets the warps w and w + 4 of a tile read the same 32 lanes).  NH = 2 doubles the softmax warps per
+    // scheduler (4 instead of 2 at D <= 128), i.e. the thread-level parallelism that hides the MUFU dispatch and the
+    // dependent-issue latencies the exponential stream is bound by; the two threads of a row agree on the running
+    // maximum through a named-barrier vote per step and a shared-memory exchange on the (rare) rescales.
+    static constexpr int NH = (QA_SPLIT != 0 && !SOLO) ? 2 : 1;
+    static constexpr int CW = BS / NH;  // score columns per softmax thread and step
     static constexpr int CTAS_PER_SM = SOLO ? 2 : 1;
     static constexpr int TMEM_COLS = SOLO ? 256 : 512;
     static constexpr bool REBALANCE = (NQ == 2) || SOLO;  // setmaxnreg: registers move to the softmax warps
-    static constexpr int REG_SOFTMAX = SOLO ? 216 : 224, REG_OTHER = SOLO ? 40 : 56;
+    // (setmaxnreg moves registers inside the allocation the CTA was launched with: 20 warps x 96 = 16 x 104 + 4 x 64)
+    static constexpr int REG_SOFTMAX = SOLO ? 216 : (NH == 2 ? 112 : 224), REG_OTHER = SOLO ? 40 : (NH == 2 ? 32 : 56);
     static constexpr int VB = V16 ? 2 : 1;          // bytes per V element
     static constexpr int QB = QK16_ ? 2 : 1;        // bytes per Q / K element
     // shared-memory tiles are stored as "boxes" whose rows are one swizzle span (<= 128 bytes) wide
@@ -156,9 +167,13 @@ struct AttnCfg {
     static constexpr int ONES_BYTES = MMASUM ? 4096 : 0;  // 32 keys x one swizzle span
     static constexpr int SMEM_ONES = O_OWN ? SMEM_O + NQ * O_TILE : SMEM_V + STAGES * V_TILE;
     static constexpr int SMEM_BAR = SMEM_ONES + ONES_BYTES;
-    static constexpr int SMEM_TOTAL = SMEM_BAR + 512 + 1024;  // + barriers + alignment slack
+    static constexpr int SMEM_XCHG = SMEM_BAR + 512;          // split softmax: one float per (tile, share, row)
+    static constexpr int XCHG_BYTES = (NH == 2) ? NQ * 2 * 128 * 4 : 0;
+    static constexpr int SMEM_TOTAL = SMEM_XCHG + XCHG_BYTES + 1024;  // + barriers + alignment slack
     static_assert(SMEM_TOTAL * CTAS_PER_SM + 1024 * CTAS_PER_SM <= 233472, "shared memory budget exceeded");
-    static constexpr int NTHREADS = (NQ * 4 + 4) * 32;  // softmax warpgroups + one warpgroup holding the MMA / TMA warps
+    static constexpr int NSOFT = NQ * 4 * NH;           // softmax warps
+    static constexpr int NTHREADS = (NSOFT + 4) * 32;   // softmax warpgroups + one warpgroup holding the MMA / TMA warps
+    static_assert(NH == 1 || DIRECT_STORE, "the split softmax writes its output rows from registers");
     // TMEM columns
     static constexpr int TM_S = 0;                        // S_t at t * 128 (64 columns)
     static constexpr int TM_P = 64;                       // P(t, b) at t * 128 + 64 + b * 32
@@ -309,8 +324,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             const int t = lane >> 1, x = lane & 1;
             if (x) mbar_init(&bars->o_full[t], 1);
             mbar_init(&bars->pv_done[t][x], 1);
-            mbar_init(&bars->p_full[t][x], 128);
-            mbar_init(x ? &bars->s_free[t] : &bars->s_full[t], x ? 128 : 1);
+            mbar_init(&bars->p_full[t][x], 128 * C::NH);
+            mbar_init(x ? &bars->s_free[t] : &bars->s_full[t], x ? 128 * C::NH : 1);
         }
         fence_barrier_init();
     }
@@ -331,7 +346,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             tma_load_4d(smem + C::SMEM_V + s * C::V_TILE + x * C::V_BOX_BYTES, &tmV, &bars->v_full[s],
                         x * (C::V_ROW / C::VB), n * BN, hkv, b, kEvictLast);
     };
-    if (warp == NQ * 4 + 1) {
+    if (warp == C::NSOFT + 1) {
         if (lane < 4) {
             mbar_init(&bars->k_full[lane], 1);
             mbar_init(&bars->k_empty[lane], NQ);  // released by every tile's MMA warp
@@ -377,9 +392,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
     // register rebalancing (two-tile configs run 384 threads -> 168 registers each at launch): the softmax
     // warpgroups keep a whole score row per thread in registers, the MMA / TMA warps need almost nothing
-    if (warp >= NQ * 4) {
+    if (warp >= C::NSOFT) {
         if constexpr (C::REBALANCE) reg_dealloc<C::REG_OTHER>();
-        if (warp == NQ * 4 + 1) {
+        if (warp == C::NSOFT + 1) {
             // =========================================================== TMA producer
             if (lane == 0) {
                 for (int n = n_pre; n < n_kv; ++n) {  // (Q and the first n_pre tiles were issued during the setup)
@@ -391,13 +406,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     load_v(n);
                 }
             }
-        } else if (warp == NQ * 4 || (NQ == 2 && warp == NQ * 4 + 2)) {
+        } else if (warp == C::NSOFT || (NQ == 2 && warp == C::NSOFT + 2)) {
             // =========================================================== MMA issuers: one warp per query tile
             // Each tile has its own chain  P_j -> PV_j -> QK_{j+2} -> S_{j+2}; a warp per tile keeps the two chains
             // independent (a single in-order issuer would couple them) and halves the per-step instruction stream.
             // The warp walks the loop converged; one elected lane issues.  Descriptors are built once: per MMA only
             // the 14-bit start-address field of the low word changes.
-            const int t = (warp - NQ * 4) >> 1;
+            const int t = (warp - C::NSOFT) >> 1;
             const int nst = n_steps(t);
             const uint32_t qk_fmt = (C::QK16 && !p.qk_fp16) ? 1u : 0u;  // f16: 0 = fp16, 1 = bf16;  f8f6f4: 0 = e4m3
             const uint32_t idesc_qk = make_idesc(qk_fmt, qk_fmt, 0, 0, BM, BS);
@@ -532,11 +547,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     } else {
         // =============================================================== softmax / correction / epilogue
         if constexpr (C::REBALANCE) reg_alloc<C::REG_SOFTMAX>();
-        const int t = warp >> 2;                       // query tile of this warpgroup
+        constexpr int NH = C::NH, CW = C::CW;
+        const int t = warp / (4 * NH);                 // query tile of this warpgroup (pair)
+        const int hf = (warp >> 2) % NH;               // which CW-column share of every step this thread owns
         const int row = ((warp & 3) << 5) | lane;      // row inside the tile == TMEM lane
         const uint32_t lane_base = uint32_t((warp & 3) * 32) << 16;
-        const uint32_t s_addr = tmem + lane_base + C::TM_S + t * 128;
-        const uint32_t p_base = tmem + lane_base + C::TM_P + t * 128;
+        const uint32_t s_addr = tmem + lane_base + C::TM_S + t * 128 + hf * CW;
+        // a thread's share of a P buffer: CW keys = CW / 2 columns of 16-bit P, CW / 4 columns of e4m3 P
+        const uint32_t p_base = tmem + lane_base + C::TM_P + t * 128 + hf * (C::V16 ? CW / 2 : CW / 4);
+        // the NH threads of a row meet at a named barrier of their own (ids 1 .. 8) and swap values through shared memory
+        const uint32_t pair_bar = 1 + t * 4 + (warp & 3);
+        float* xchg = reinterpret_cast<float*>(smem + C::SMEM_XCHG) + (t * 2) * 128 + row;  // [t][share][row]
         const uint32_t o_addr = tmem + lane_base + C::TM_O + (NQ == 2 ? t * 128 : 0);
         const uint32_t l_addr = tmem + lane_base + C::TM_L + t * 128;
         const int row_g = m0 + t * BM + row;
@@ -557,39 +578,39 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const int my_steps = n_steps(t);
 
         // per-column K scales (token mode), applied to the raw scores of step j
-        auto kscale = [&](const int j, float (&s)[BS]) {
+        auto kscale = [&](const int j, float (&s)[C::CW]) {
             if constexpr (TOKEN) {
-                const int col0 = j * BS;
-                if (col0 + BS <= p.Skv && (p.Skv & 3) == 0) {  // rows of scale_k stay 16-byte aligned
+                const int col0 = j * BS + hf * CW;
+                if (col0 + CW <= p.Skv && (p.Skv & 3) == 0) {  // rows of scale_k stay 16-byte aligned
 #pragma unroll
-                    for (int i = 0; i < BS; i += 4) {
+                    for (int i = 0; i < CW; i += 4) {
                         float4 k4 = __ldg(reinterpret_cast<const float4*>(sk_row + col0 + i));
                         s[i] *= k4.x, s[i + 1] *= k4.y, s[i + 2] *= k4.z, s[i + 3] *= k4.w;
                     }
                 } else {
 #pragma unroll
-                    for (int i = 0; i < BS; ++i) s[i] *= __ldg(sk_row + min(col0 + i, p.Skv - 1));
+                    for (int i = 0; i < CW; ++i) s[i] *= __ldg(sk_row + min(col0 + i, p.Skv - 1));
                 }
             }
         };
         // causal / ragged mask of step j.  Only the trailing steps of a tile can need it (the ragged tail is the last
         // step, the causal diagonal the last two), so it is instantiated in the tail loop only: the main loop below
         // carries no mask code at all and stays a compact straight line for the instruction cache.
-        auto mask = [&](const int j, float (&s)[BS]) {
-            const int col0 = j * BS;
-            const bool tail = col0 + BS > p.Skv;
-            const bool diag = CAUSAL && (col0 + BS - 1 > m0 + t * BM);
+        auto mask = [&](const int j, float (&s)[C::CW]) {
+            const int col0 = j * BS + hf * CW;
+            const bool tail = col0 + CW > p.Skv;
+            const bool diag = CAUSAL && (col0 + CW - 1 > m0 + t * BM);
             if (tail || diag) {
                 const int lim = CAUSAL ? min(p.Skv - 1, row_g) : (p.Skv - 1);  // last visible column
 #pragma unroll
-                for (int i = 0; i < BS; ++i)
+                for (int i = 0; i < CW; ++i)
                     if (col0 + i > lim) s[i] = -INFINITY;
             }
         };
         // first step whose scores need the mask (every later one does too)
         const int j_mask = CAUSAL ? min(p.Skv / BS, (m0 + t * BM) / BS) : p.Skv / BS;
         // row maximum of sixteen columns folded into two running maxima (two chains per call site -> four in flight)
-        auto max16 = [&](const float (&s)[BS], int q, float& ma, float& mb) {
+        auto max16 = [&](const float (&s)[C::CW], int q, float& ma, float& mb) {
 #pragma unroll
             for (int i = 16 * q; i < 16 * q + 16; i += 4) {
                 ma = fmaxf(ma, fmaxf(s[i], s[i + 1]));
@@ -597,9 +618,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             }
         };
         // rare: the running maximum of some row of this warp grew by more than 2^TAU -> rescale O (rolled: cold code)
-        auto rescale_o = [&](const float alpha) {
+        auto rescale_o = [&](const float alpha) {  // (the NH threads of a row take D / NH columns each)
 #pragma unroll 1
-            for (int cc = 0; cc < D; cc += 32) {
+            for (int cc = hf * (D / NH); cc < (hf + 1) * (D / NH); cc += 32) {
                 float o[32];
                 tmem_ld_x32(o_addr + cc, o);
                 tmem_ld_wait();
@@ -608,9 +629,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 tmem_st_x32(o_addr + cc, o);
             }
             if constexpr (C::MMASUM) {  // the row sum lives beside O and is rescaled with it
-                float lv = tmem_ld_x1(l_addr);
-                tmem_ld_wait();
-                tmem_st_x1(l_addr, lv * alpha);
+                if (hf == 0) {
+                    float lv = tmem_ld_x1(l_addr);
+                    tmem_ld_wait();
+                    tmem_st_x1(l_addr, lv * alpha);
+                }
             }
             tmem_st_wait();
         };
@@ -621,18 +644,26 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         // exponentials; it returns that maximum.  The code between the few waits is straight-line on purpose: every
         // branch is a scheduling barrier at which the exp pipeline of this warp drains.
         //   MASKED (compile time): S_{j+1} may need the causal / ragged mask;  `last`: there is no S_{j+1}.
-        constexpr int LOADQ = QA_LOADQ;  // quad index (of 16) before which the load of S_{j+1} is issued
-        static_assert(LOADQ >= 2 && LOADQ <= 12 && LOADQ % 2 == 0, "LOADQ");
+        constexpr int NQD = CW / 4;             // quads of columns per thread and step (16, or 8 with two threads per row)
+        constexpr int LOADQ = QA_LOADQ / NH;    // quad index (of NQD) before which the load of S_{j+1} is issued
+        static_assert(QA_LOADQ >= 2 && QA_LOADQ <= 12 && QA_LOADQ % 2 == 0, "LOADQ");
         //   `need` (warp-uniform): some row of the warp has outgrown its stale maximum, as decided near the END of the
         //   previous step (see below) - so the common case enters the exponentials with nothing to wait for.
-        auto step = [&](const int j, float (&s)[BS], float (&s_next)[BS], const float mx, bool& need, auto mask_tag,
+        auto step = [&](const int j, float (&s)[C::CW], float (&s_next)[C::CW], const float mx, bool& need, auto mask_tag,
                         const bool last) -> float {
             constexpr bool MASKED = decltype(mask_tag)::value;
             QA_STAMP(t, j, 0);
             bool p_prev_pending = j > 0;  // P_{j-1} is stored but not yet published (see below)
             // lazy rescale: keep the stale max while the true max has grown by < 2^TAU
             if (__builtin_expect(need, 0)) {
-                const float m_new = fmaxf(m_used, mx);
+                float m_new = fmaxf(m_used, mx);
+                if constexpr (NH == 2) {
+                    // the row's other thread holds the maximum of the other columns: swap through shared memory.  (The
+                    // slot is rewritten at the earliest on the next rescale, and a vote barrier lies in between.)
+                    xchg[hf * 128] = mx;
+                    named_bar_sync(pair_bar, 64);
+                    m_new = fmaxf(m_new, xchg[(hf ^ 1) * 128]);
+                }
                 const float alpha = ex2_approx((m_used - m_new) * c);  // 0 on the first step
                 m_used = m_new;
                 if constexpr (!C::MMASUM) la.x *= alpha, la.y *= alpha, lb.x *= alpha, lb.y *= alpha;
@@ -660,7 +691,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 if (pair_uses_poly(i, C::POLY_NUM)) return exp2_poly<C::POLY_DEG>(x);
                 return make_float2(ex2_approx(x.x), ex2_approx(x.y));
             };
-            uint32_t pw[C::V16 ? BS / 2 : BS / 4], pw_lo[C::PMODE == QA_P_E4M3_HILO ? BS / 4 : 1];
+            uint32_t pw[C::V16 ? CW / 2 : CW / 4], pw_lo[C::PMODE == QA_P_E4M3_HILO ? CW / 4 : 1];
             // four columns -> P words (and, unless the tensor core sums the rows of P, the running row sum)
             auto exp_quad = [&](int i) {
                 if constexpr (C::H2POLY) {
@@ -692,7 +723,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 }
             };
 
-            constexpr int PUBQ = QA_PUBQ, LDW = QA_LDWAITQ, PROBEQ = QA_PROBEQ;
+            constexpr int PUBQ = (QA_PUBQ / NH) > 0 ? QA_PUBQ / NH : 1, LDW = (QA_LDWAITQ / NH) > 0 ? QA_LDWAITQ / NH : 1;
+            constexpr int PROBEQ = QA_PROBEQ / NH;
             static_assert(PUBQ >= 1 && PUBQ <= LOADQ - PROBEQ && LDW >= 1, "quad schedule");
 #pragma unroll
             for (int i = 0; i < PUBQ; ++i) exp_quad(i);
@@ -715,7 +747,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 QA_STAMP(t, j, 5);
                 if (!s_ready) mbar_wait(&bars->s_full[t], (j + 1) & 1);
                 tc_fence_after();
-                tmem_ld_f64(s_addr, s_next);
+                if constexpr (NH == 1) tmem_ld_f64(s_addr, s_next);
+                else tmem_ld_x32(s_addr, s_next);
                 QA_STAMP(t, j, 2);
 #pragma unroll
                 for (int i = LOADQ; i < LOADQ + LDW; ++i) exp_quad(i);
@@ -729,37 +762,43 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 // pieces in all; the rescale decision for step j + 1 (a warp vote) is taken before those last quads, whose
                 // exponentials hide its latency
                 constexpr int DECQ = QA_DECIDEQ;
-                constexpr int REST = 16 - LDW - LOADQ - DECQ;  // quads carrying a piece of the maximum
+                constexpr int REST = NQD - LDW - LOADQ - DECQ;  // quads carrying a piece of the maximum
                 static_assert(REST >= 1, "LOADQ / QA_DECIDEQ leave no room for the row maximum");
-                constexpr int PER = (4 + REST - 1) / REST;    // pieces per quad
+                constexpr int NPIECE = CW / 16;               // 16-column pieces of the row maximum
+                constexpr int PER = (NPIECE + REST - 1) / REST;  // pieces per quad
 #pragma unroll
-                for (int i = LOADQ + LDW; i < 16 - DECQ; ++i) {
+                for (int i = LOADQ + LDW; i < NQD - DECQ; ++i) {
                     exp_quad(i);
 #pragma unroll
                     for (int q = 0; q < PER; ++q) {
                         const int piece = (i - LOADQ - LDW) * PER + q;
-                        if (piece < 4) max16(s_next, piece, ma, mb);
+                        if (piece < NPIECE) max16(s_next, piece, ma, mb);
                     }
                 }
-                need = __any_sync(0xffffffffu, (fmaxf(ma, mb) - m_used) * c > C::TAU);
+                if constexpr (NH == 1) {
+                    need = __any_sync(0xffffffffu, (fmaxf(ma, mb) - m_used) * c > C::TAU);
+                } else {
+                    // both threads of a row must take the rescale path together: an OR over the 64 threads of the pair
+                    need = bar_red_or(pair_bar, 64, (fmaxf(ma, mb) - m_used) * c > C::TAU);
+                }
 #pragma unroll
-                for (int i = 16 - DECQ; i < 16; ++i) exp_quad(i);
+                for (int i = NQD - DECQ; i < NQD; ++i) exp_quad(i);
             } else {
                 need = false;
 #pragma unroll
-                for (int i = LOADQ - PROBEQ; i < 16; ++i) exp_quad(i);
+                for (int i = LOADQ - PROBEQ; i < NQD; ++i) exp_quad(i);
                 // P buffer reuse: PV_{j-2} must have drained it.  Seeing S_{j+1} (issued after PV_{j-2}, in-order
                 // tensor pipe) proves that in every other step; the last one waits for PV_{j-1} explicitly.
                 if (j >= 2) mbar_wait(&bars->pv_done[t][(j - 1) & 1], ((j - 1) >> 1) & 1);
             }
             const uint32_t p_addr = p_base + (j & 1) * 32;
             if constexpr (C::PMODE == QA_P_E4M3) {
-                tmem_st_u16(p_addr, pw);
+                tmem_st_words<CW / 4>(p_addr, pw);
             } else if constexpr (C::PMODE == QA_P_E4M3_HILO) {
-                tmem_st_u16(p_addr, pw);
-                tmem_st_u16(p_addr + C::TM_P_LO, pw_lo);
+                tmem_st_words<CW / 4>(p_addr, pw);
+                tmem_st_words<CW / 4>(p_addr + C::TM_P_LO, pw_lo);
             } else {
-                tmem_st_u32(p_addr, pw);
+                tmem_st_words<CW / 2>(p_addr, pw);
             }
             if (last) {  // nothing left to hide the store behind
                 tmem_st_wait();
@@ -777,14 +816,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             }
         }
 #endif
-        float s_a[BS], s_b[BS];
+        float s_a[CW], s_b[CW];
         float mx;
         QA_STAMP(t, 78, 1);
         {   // S_0
             mbar_wait(&bars->s_full[t], 0);
             QA_STAMP(t, 78, 2);
             tc_fence_after();
-            tmem_ld_f64(s_addr, s_a);
+            if constexpr (NH == 1) tmem_ld_f64(s_addr, s_a);
+            else tmem_ld_x32(s_addr, s_a);
             tmem_ld_wait();
             tc_fence_before();
             mbar_arrive(&bars->s_free[t]);
@@ -792,7 +832,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             mask(0, s_a);
             float ma = -INFINITY, mb = -INFINITY;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) max16(s_a, q, ma, mb);
+            for (int q = 0; q < CW / 16; ++q) max16(s_a, q, ma, mb);
             mx = fmaxf(ma, mb);
         }
         {
@@ -811,10 +851,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             for (; j < my_steps; ++j) {
                 mx = step(j, s_a, s_b, mx, need, true_type{}, j + 1 == my_steps);
 #pragma unroll
-                for (int i = 0; i < BS; ++i) s_a[i] = s_b[i];
+                for (int i = 0; i < CW; ++i) s_a[i] = s_b[i];
             }
         }
         float l = (la.x + la.y) + (lb.x + lb.y);
+        if constexpr (NH == 2 && !C::MMASUM) {  // the row sum is the sum of the two threads' shares
+            named_bar_sync(pair_bar, 64);  // (the other thread may still be reading a maximum from the slot)
+            xchg[hf * 128] = l;
+            named_bar_sync(pair_bar, 64);
+            l += xchg[(hf ^ 1) * 128];
+        }
         QA_STAMP(t, 78, 3);
 
         // ---------------------------------------------------------------- epilogue: O / l -> 16 bit -> smem -> TMA
@@ -832,8 +878,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         // 32-byte sector per store.  Nothing to stage, fence or wait for - the CTA is free to retire as soon as the
         // stores are issued, where the shared-memory + TMA route kept it alive until the bulk store had read the tile.
         uint8_t* o_row = static_cast<uint8_t*>(p.out) + (size_t(bh) * p.Sq + min(row_g, p.Sq - 1)) * (D * 2);
+        // (with NH threads per row each writes its D / NH columns: still whole 32-byte sectors)
 #pragma unroll
-        for (int cc = 0; cc < D; cc += 32) {
+        for (int c0 = 0; c0 < D / NH; c0 += 32) {
+            const int cc = hf * (D / NH) + c0;
             float o[32];
             tmem_ld_x32(o_addr + cc, o);
             tmem_ld_wait();
@@ -848,7 +896,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 st_global_32B(o_row + cc * 2 + 32, w + 8);
             }
         }
-        if (p.lse != nullptr && row_g < p.Sq)
+        if (p.lse != nullptr && row_g < p.Sq && hf == 0)
             p.lse[size_t(bh) * p.Sq + row_g] = (m_used * c + (__log2f(l) - C::KOFF)) * 0.6931471805599453f;
 #else
         uint8_t* o_smem = smem + C::SMEM_O + t * C::O_TILE;

@@ -436,6 +436,31 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// barrier with an OR reduction over the participating threads' predicates (all of them receive the result)
+__device__ __forceinline__ bool bar_red_or(uint32_t id, uint32_t nthreads, bool pred) {
+    uint32_t r;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pin, pout;\n\t"
+        "setp.ne.u32 pin, %1, 0;\n\t"
+        "bar.red.or.pred pout, %2, %3, pin;\n\t"
+        "selp.u32 %0, 1, 0, pout;\n\t"
+        "}\n"
+        : "=r"(r)
+        : "r"(uint32_t(pred)), "r"(id), "r"(nthreads)
+        : "memory");
+    return r != 0;
+}
+// N words (8 / 16 / 32) of a thread's registers -> N consecutive TMEM columns of its lane
+template <int N>
+__device__ __forceinline__ void tmem_st_words(uint32_t taddr, const uint32_t* r);
+template <>
+__device__ __forceinline__ void tmem_st_words<8>(uint32_t taddr, const uint32_t* r) { tmem_st_u8(taddr, r); }
+template <>
+__device__ __forceinline__ void tmem_st_words<16>(uint32_t taddr, const uint32_t* r) { tmem_st_u16(taddr, r); }
+template <>
+__device__ __forceinline__ void tmem_st_words<32>(uint32_t taddr, const uint32_t* r) { tmem_st_u32(taddr, r); }
+
 template <uint32_t N>
 __device__ __forceinline__ void reg_dealloc() {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));

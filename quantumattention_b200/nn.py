@@ -96,9 +96,17 @@ def _device_supported(index: int) -> Tuple[bool, str]:
     return True, ""
 
 
+@torch.compiler.assume_constant_result
+def _device_supported_traced(index: Optional[int]) -> Tuple[bool, str]:
+    # (under dynamo the capability query would otherwise be traced INTO the graph as a call of its own)
+    return _device_supported(index if index is not None else torch.cuda.current_device())
+
+
 def _pre_check(device: torch.device) -> Tuple[bool, str]:
     if device.type != "cuda":
         return False, f"Expected device to be on a CUDA device, but got device: {device} instead."
+    if torch.compiler.is_dynamo_compiling():
+        return _device_supported_traced(device.index)
     return _device_supported(device.index if device.index is not None else torch.cuda.current_device())
 
 

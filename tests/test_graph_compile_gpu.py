@@ -71,18 +71,31 @@ def test_quantise_ops_are_the_native_quantiser():
 
 
 def test_opcheck_registered_ops():
-    """torch.library.opcheck: schema (no hidden mutation / aliasing) and fake-tensor agreement of every custom op."""
+    """torch.library.opcheck on every custom op: fake-tensor agreement (shapes, dtypes, strides, devices of the real
+    and the fake implementation) for all of them, and the schema test (no hidden mutation / aliasing) where torch can
+    run it - its input comparison has no float8 kernels, so for the ops that touch e4m3 tensors the mutation check is
+    done here on the bytes."""
     q, k, v = _qkv(1, 2, 256, 128, seed=2)
     q8, k8, sq, sk = torch.ops.quantum_attn.quantize_qk_fp8(q, k, False)
-    utils = ("test_schema", "test_faketensor")
-    torch.library.opcheck(torch.ops.quantum_attn.fp8_attention_forward.default, (q8, k8, v, sq, sk),
-                          {"is_causal": True}, test_utils=utils)
+    fake = ("test_faketensor",)
     torch.library.opcheck(torch.ops.quantum_attn.attention_forward.default, (q, k, v), {"is_causal": False},
-                          test_utils=utils)
-    torch.library.opcheck(torch.ops.quantum_attn.dynamically_quantize_fp8.default, (q, [2, 3]), test_utils=utils)
-    torch.library.opcheck(torch.ops.quantum_attn.dynamically_quantize_fp8.default, (q, [-1]), test_utils=utils)
-    torch.library.opcheck(torch.ops.quantum_attn.quantize_qk_fp8.default, (q, k, False), test_utils=utils)
-    torch.library.opcheck(torch.ops.quantum_attn.quantize_qk_fp8.default, (q, k, True), test_utils=utils)
+                          test_utils=("test_schema", "test_faketensor"))
+    torch.library.opcheck(torch.ops.quantum_attn.fp8_attention_forward.default, (q8, k8, v, sq, sk),
+                          {"is_causal": True}, test_utils=fake)
+    torch.library.opcheck(torch.ops.quantum_attn.dynamically_quantize_fp8.default, (q, [2, 3]), test_utils=fake)
+    torch.library.opcheck(torch.ops.quantum_attn.dynamically_quantize_fp8.default, (q, [-1]), test_utils=fake)
+    torch.library.opcheck(torch.ops.quantum_attn.quantize_qk_fp8.default, (q, k, False), test_utils=fake)
+    torch.library.opcheck(torch.ops.quantum_attn.quantize_qk_fp8.default, (q, k, True), test_utils=fake)
+    # mutates_args=(): inputs come back bit-identical, outputs alias none of them
+    snap = [t.clone() for t in (q, k, v, q8.view(torch.uint8), k8.view(torch.uint8), sq, sk)]
+    out = torch.ops.quantum_attn.fp8_attention_forward(q8, k8, v, sq, sk, is_causal=True)
+    a8, b8, sa, sb = torch.ops.quantum_attn.quantize_qk_fp8(q, k, True)
+    t8, ts = torch.ops.quantum_attn.dynamically_quantize_fp8(v, [2, 3])
+    torch.cuda.synchronize()
+    for before, after in zip(snap, (q, k, v, q8.view(torch.uint8), k8.view(torch.uint8), sq, sk)):
+        assert torch.equal(before, after)
+    ins = {t.data_ptr() for t in (q, k, v, q8, k8, sq, sk)}
+    assert not ({t.data_ptr() for t in (out, a8, b8, sa, sb, t8, ts)} & ins)
 
 
 # ------------------------------------------------------------------------------------------------ torch.compile
@@ -108,9 +121,10 @@ def test_compiled_graph_calls_the_hand_written_kernels(method):
     fn = quantum_attn.fp8_attn_func if method == "head-wise" else quantum_attn.fp8_token_wise_attn_func
     eager = fn(q, k, v, is_causal=True)
     names, out = _graph_ops(fn, q, k, v, is_causal=True)
-    assert names.count("quantum_attn.quantize_qk_fp8.default") == 1, names
-    assert names.count("quantum_attn.fp8_attention_forward.default") == 1, names
-    assert not [n for n in names if n.startswith("aten.")], names
+    assert sum(n.startswith("quantum_attn.quantize_qk_fp8") for n in names) == 1, names
+    assert sum(n.startswith("quantum_attn.fp8_attention_forward") for n in names) == 1, names
+    # nothing else but the unpacking of the quantiser's outputs: no aten arithmetic, no device query
+    assert all(n.startswith("quantum_attn.") or "getitem" in n for n in names), names
     assert torch.equal(out, eager)
     compiled = torch.compile(fn, backend="aot_eager", fullgraph=True)
     compiled(q, k, v, is_causal=True)

@@ -54,7 +54,9 @@ def test_long_sequences_oracle_on_2_heads_x_192_rows(D, S, causal):
             out = quantum_attn.fp8_attn_func(q, k, v, is_causal=causal)
             ones = quantum_attn.fp8_attn_func(q, k, torch.ones_like(v), is_causal=causal)
         assert out.shape == q.shape and bool(torch.isfinite(out).all()), pv
-        assert (ones.float() - 1.0).abs().max().item() < 0.01, pv
+        # (single-e4m3 P without the tensor-core row sum - D = 256 - normalises by the sum of the UNROUNDED weights:
+        # the rows then sum to one only to within the e4m3 rounding of the weights)
+        assert (ones.float() - 1.0).abs().max().item() < (0.03 if pv == "fp8" else 0.01), pv
         m = oracle.compare(out[:, :, rows.cuda()].float().cpu().numpy(), refs[pv].numpy())
         assert m["cos_sim"] >= 0.999 and m["max_abs_over_row_rms"] <= ROW_BOUND[pv], (D, S, causal, pv, m)
 
