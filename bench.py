@@ -250,19 +250,12 @@ def seq_sharded_block(dev, rank, world, dist, steps, warmup):
         dist.barrier()
         torch.cuda.synchronize()
 
-    transport_error = None
-    try:
-        for _ in range(max(2, warmup // 4)):
-            out = parallel.ring_fp8_attention(*loc)
-        barrier()
-    except Exception as e:  # e.g. peer transport unavailable on this box: fall back to NCCL and say so
-        if transport == "nccl":
-            raise
-        transport_error = repr(e)[:200]
-        os.environ["QA_SEQ_TRANSPORT"] = transport = "nccl"
-        for _ in range(max(2, warmup // 4)):
-            out = parallel.ring_fp8_attention(*loc)
-        barrier()
+    for _ in range(max(2, warmup // 4)):
+        out = parallel.ring_fp8_attention(*loc)
+    barrier()
+    v_item = 2 if pv_mode == "16bit" else 1
+    transport, comm = parallel.resolve_transport(transport, None, loc[0], loc[1], loc[2], v_item)  # what "auto" became
+    transport_error = parallel.last_transport_error()
     n = max(5, min(steps, 30))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = _native.launch_total
@@ -295,22 +288,31 @@ def seq_sharded_block(dev, rank, world, dist, steps, warmup):
                          "first: they travel); transfer_exposed = time the compute stream waited for blocks; attention = "
                          "the per-head-group launches")
 
-    # the transfer alone: every head group's blocks, nothing else running
-    v_item = 2 if pv_mode == "16bit" else 1
+    # the transfer alone, by the transport in use: every head group's blocks, nothing else running
     wire_bytes = (world - 1) * B * H * S_loc * D * (1 + v_item)  # received per rank per step
-    k_loc = torch.empty((B, H, S_loc, D), dtype=torch.uint8, device=dev)
-    v_loc = torch.empty((B, H, S_loc, D * v_item), dtype=torch.uint8, device=dev)
-    k_all = torch.empty((B, H, S, D), dtype=torch.uint8, device=dev)
-    v_all = torch.empty((B, H, S, D * v_item), dtype=torch.uint8, device=dev)
     chunks = parallel.head_chunks(B, H, S_loc)
     gather_ms = None
     try:
-        for rep in range(4):
-            barrier()
-            if rep == 1:
-                e0.record()
-            for lo, hi in chunks:
-                parallel._nccl_gather_heads([k_loc, v_loc], [k_all, v_all], lo, hi, None).wait()
+        if transport == "peer":
+            main = torch.cuda.current_stream()
+            for rep in range(4):
+                barrier()
+                if rep == 1:
+                    e0.record()
+                for ev in comm.pull(chunks):
+                    main.wait_event(ev)
+        else:
+            k_loc = torch.empty((B, H, S_loc, D), dtype=torch.uint8, device=dev)
+            v_loc = torch.empty((B, H, S_loc, D * v_item), dtype=torch.uint8, device=dev)
+            k_all = torch.empty((B, H, S, D), dtype=torch.uint8, device=dev)
+            v_all = torch.empty((B, H, S, D * v_item), dtype=torch.uint8, device=dev)
+            for rep in range(4):
+                barrier()
+                if rep == 1:
+                    e0.record()
+                for lo, hi in chunks:
+                    parallel._nccl_gather_heads([k_loc, v_loc], [k_all, v_all], lo, hi, None).wait()
+            del k_loc, v_loc, k_all, v_all
         e1.record()
         barrier()
         tg = torch.tensor([e0.elapsed_time(e1) / 3], device=dev, dtype=torch.float64)
@@ -319,7 +321,6 @@ def seq_sharded_block(dev, rank, world, dist, steps, warmup):
     except Exception as e:
         gather_ms = None
         transport_error = (transport_error or "") + " gather probe: " + repr(e)[:120]
-    del k_loc, v_loc, k_all, v_all
 
     # accuracy of every P mode on a slice, and the same call on one GPU (rank 0 only; the others wait at the barrier)
     accuracy, one_gpu_ms = {}, None
@@ -374,8 +375,9 @@ def seq_sharded_block(dev, rank, world, dist, steps, warmup):
                  "what": "e4m3 K + " + ("16-bit V" if v_item == 2 else "e4m3 V") + " blocks of the other ranks",
                  "gather_alone_ms": gather_ms,
                  "gather_alone_gbs": (wire_bytes / (gather_ms * 1e-3) / 1e9) if gather_ms else None,
-                 "gather_alone_how": "grouped NCCL all-gathers of every head group back to back, nothing else running, "
-                                     "max over ranks (measured reference on this pool: 770 GB/s peer copy per direction)"},
+                 "gather_alone_how": ("copy-engine pulls (qa_copy_2d from peer-mapped symmetric memory)" if transport == "peer"
+                                      else "grouped NCCL all-gathers") + " of every head group back to back, nothing else "
+                                     "running, max over ranks (measured reference on this pool: 770 GB/s peer copy per direction)"},
         "time_split": split,
         "accuracy": accuracy,
         "accuracy_against": "fp64 softmax(QK^T)V on the dequantised e4m3 Q, K and the mode's V (16-bit for '16bit', "

@@ -100,6 +100,12 @@ constexpr float kLog2e = 1.4426950408889634f;
 #ifndef QA_DECIDEQ
 #define QA_DECIDEQ 1   // quads of exponentials left when the rescale decision for the next step is taken
 #endif
+#ifndef QA_QTMEM
+#define QA_QTMEM 1     // e4m3 Q in tensor memory, Q K^T as a TS-form MMA: 1 = where it pays (D = 256), 2 = everywhere, 0 = nowhere
+#endif
+#ifndef QA_FORCE_PBUFS1
+#define QA_FORCE_PBUFS1 0  // experiment: one P buffer without Q in TMEM (measured: C2 172.4 -> 180.6 us)
+#endif
 #ifndef QA_SPLIT
 #define QA_SPLIT 0     // 1: TWO softmax threads per query row (each owns half of a step's 64 columns): 4 softmax warps per scheduler
 #endif
@@ -119,6 +125,18 @@ struct AttnCfg {
     // in 128-row units.
     static constexpr bool SOLO = (QA_SOLO != 0) && D_ <= 128 && !QK16_ && !(PMODE_ == QA_P_16BIT);
     static constexpr int NQ = (D_ <= 128 && !SOLO) ? 2 : 1;  // O for two tiles does not fit TMEM at D = 256
+    // Q in TENSOR MEMORY (D = 256).  An SS-form tcgen05.mma (A and B from shared memory) first loads its A operand - 128
+    // rows x 32 bytes - which costs ~43 cycles per MMA on top of the N / 2 cycles of the product itself: measured on
+    // B200 (scripts/ubench/mma_rate.cu) M128 x N64 x K32 takes 75 cycles from shared memory and 42 with A in TMEM.  Q
+    // never changes during a tile, so the softmax threads put their query row into TMEM once (thread r = lane r, D
+    // bytes = D / 4 columns, straight from global memory) and Q K^T runs as a TS-form MMA like P V does.  At D = 256 a
+    // CTA holds ONE query tile, its 8 + 4 MMAs per step bound the step, and the TMEM columns are there: 633 -> 600 us
+    // (16-bit P) / 510 -> 477 us (e4m3 P) on B16 S8192, causal 316 -> 289 us.  At D <= 128 the two tiles of a CTA
+    // leave no columns for Q unless P goes down to one buffer, and there the tensor pipe is not what bounds the step:
+    // measured SLOWER with Q in TMEM (C2 168.6 -> 184.8 us; one P buffer alone 172.4 -> 180.6 us), so those shapes
+    // keep Q in shared memory (-DQA_QTMEM=2 forces the TMEM form everywhere, =0 nowhere).  Not for 16-bit Q.
+    static constexpr bool QTMEM = (QA_QTMEM == 2 || (QA_QTMEM == 1 && D_ == 256)) && (QA_DIRECT_STORE != 0) && !QK16_ && !SOLO;
+    static constexpr int PBUFS = ((QTMEM && D_ != 256) || QA_FORCE_PBUFS1) ? 1 : 2;  // (D = 256: one tile, both P buffers fit beside Q)
     // NH softmax threads share a query row: thread `hf` of a row owns columns [hf * CW, (hf + 1) * CW) of every 64-key
     // step (TMEM lets the warps w and w + 4 of a tile read the same 32 lanes).  NH = 2 doubles the softmax warps per
     // scheduler (4 instead of 2 at D <= 128), i.e. the thread-level parallelism that hides the MUFU dispatch and the
@@ -140,7 +158,7 @@ struct AttnCfg {
     static constexpr int V_ROW = (D_ * VB) < 128 ? (D_ * VB) : 128;
     static constexpr int V_BOXES = D_ * VB / V_ROW;
     static constexpr int V_BOX_BYTES = V_ROW * BN;
-    static constexpr int Q_TILE = BM * D_ * QB;
+    static constexpr int Q_TILE = QTMEM ? 0 : BM * D_ * QB;
     static constexpr int K_TILE = BN * D_ * QB;
     static constexpr int V_TILE = BN * D_ * VB;
     static constexpr int O_BOXES = D_ / 64;  // 16-bit output, 64 elements = 128 bytes per box row
@@ -148,7 +166,7 @@ struct AttnCfg {
     static constexpr bool DIRECT_STORE = (QA_DIRECT_STORE != 0);
     static constexpr int STAGES = SOLO ? (D_ == 64 ? 4 : 2)
                                   : QK16_ ? (D_ == 64 ? 4 : (D_ == 128 ? 2 : 1))
-                                          : ((D_ == 64) ? 4 : (D_ == 128 ? ((V16 && !DIRECT_STORE) ? 2 : 3) : 2));
+                                          : ((D_ == 64) ? 4 : (D_ == 128 ? ((V16 && !DIRECT_STORE) ? 2 : (QTMEM ? 4 : 3)) : 2));
     static constexpr int SMEM_Q = 0;
     static constexpr int SMEM_K = SMEM_Q + NQ * Q_TILE;
     static constexpr int SMEM_V = SMEM_K + STAGES * K_TILE;
@@ -180,6 +198,9 @@ struct AttnCfg {
     static constexpr int TM_O = SOLO ? 128 : 256;         // O_t at 256 + t * 128 (D <= 128), single O at D = 256; SOLO: 128
     static constexpr int TM_P_LO = 16;                    // hi/lo mode: second P tile 16 columns after the first
     static constexpr int TM_L = 80;                       // MMASUM: L_t at t * 128 + 80 (16 columns, column 0 is read)
+    // QTMEM: Q_t (D / 4 columns) behind the single P buffer: t * 128 + 96 (D <= 128), 128 at D = 256 (one tile: room)
+    static constexpr int TM_Q = (D_ == 256) ? 128 : 96;
+
     // softmax range management: p' = 2^KOFF * exp2(s - m_used), m_used may lag the true max by <= TAU (log2 units)
     static constexpr float KOFF = V16 ? 0.f : 4.f;
     static constexpr float TAU = V16 ? 8.f : 4.f;
@@ -204,6 +225,8 @@ struct AttnParams {
     const float* scale_v;
     float* lse;
     void* out;  // dense [B, Hq, Sq, D], 16 bit
+    const uint8_t* q;            // QTMEM: e4m3 Q and its (batch, head, row) strides in bytes
+    long long q_sb, q_sh, q_sr;
     int B, Hq, Hkv, Sq, Skv;
     int causal;
     float sm_scale_log2;  // sm_scale * log2(e)
@@ -353,7 +376,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             mbar_init(&bars->v_full[lane], 1);
             mbar_init(&bars->v_empty[lane], NQ);
         } else if (lane < 4 + NQ) {
-            mbar_init(&bars->q_full[lane - 4], 1);
+            mbar_init(&bars->q_full[lane - 4], C::QTMEM ? 128 : 1);  // QTMEM: the tile's 128 rows, each put there by its thread
         }
         fence_barrier_init();
         __syncwarp();
@@ -363,12 +386,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             tma_prefetch_desc(&tmV);
             tma_prefetch_desc(&tmO);
             griddep_wait();
-            for (int t = 0; t < NQ; ++t) {
-                mbar_arrive_expect_tx(&bars->q_full[t], C::Q_TILE);
-                for (int x = 0; x < C::QK_BOXES; ++x)
-                    tma_load_4d(smem + C::SMEM_Q + t * C::Q_TILE + x * C::QK_BOX_BYTES, &tmQ, &bars->q_full[t],
-                                x * (C::QK_ROW / C::QB), m0 + t * BM, h, b, kEvictFirst);
-                if (t == 0) load_kv(0);  // K tile 0 right behind the first Q tile: S_0 needs exactly these two
+            if constexpr (C::QTMEM) {
+                load_kv(0);
+            } else {
+                for (int t = 0; t < NQ; ++t) {
+                    mbar_arrive_expect_tx(&bars->q_full[t], C::Q_TILE);
+                    for (int x = 0; x < C::QK_BOXES; ++x)
+                        tma_load_4d(smem + C::SMEM_Q + t * C::Q_TILE + x * C::QK_BOX_BYTES, &tmQ, &bars->q_full[t],
+                                    x * (C::QK_ROW / C::QB), m0 + t * BM, h, b, kEvictFirst);
+                    if (t == 0) load_kv(0);  // K tile 0 right behind the first Q tile: S_0 needs exactly these two
+                }
             }
             load_v(0);
             for (int n = 1; n < n_pre; ++n) {
@@ -426,6 +453,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             constexpr int KEYS_PER_PV = C::V16 ? 16 : 32;
             const uint32_t s_t = tmem + C::TM_S + t * 128;
             const uint32_t p_t0 = tmem + C::TM_P + t * 128;
+            const uint32_t q_t = tmem + C::TM_Q + t * 128;  // QTMEM: K slice k of Q_t = 8 columns at q_t + 8 k
             const uint32_t o_t = tmem + C::TM_O + (NQ == 2 ? t * 128 : 0);
             const uint32_t l_t = tmem + C::TM_L + t * 128;
             constexpr uint32_t idesc_l = make_idesc(0, 0, 0, 1, BM, 16);
@@ -438,13 +466,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 for (int k = 0; k < D * C::QB / 32; ++k) {  // one MMA per 32-byte K slice (32 e4m3 / 16 bf16 elements)
                     if constexpr (C::QK16)
                         umma_f16_ss(s_t, q_desc + (qk_koff<C>(k) >> 4), bd + (qk_koff<C>(k) >> 4), idesc_qk, k > 0);
+                    else if constexpr (C::QTMEM)
+                        umma_f8_ts(s_t, q_t + k * 8, bd + (qk_koff<C>(k) >> 4), idesc_qk, k > 0);
                     else
                         umma_f8_ss(s_t, q_desc + (qk_koff<C>(k) >> 4), bd + (qk_koff<C>(k) >> 4), idesc_qk, k > 0);
                 }
             };
             // O_t (+)= P(t, half) . V[64 keys]
             auto issue_pv = [&](int stage, int half, bool acc) {
-                const uint32_t p_t = p_t0 + half * 32;
+                const uint32_t p_t = p_t0 + (C::PBUFS == 2 ? half * 32 : 0);
                 const uint64_t bd = v_desc0 + uint64_t((stage * C::V_TILE + half * (BS * C::V_ROW)) >> 4);
 #pragma unroll
                 for (int k = 0; k < BS / KEYS_PER_PV; ++k) {
@@ -787,11 +817,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 need = false;
 #pragma unroll
                 for (int i = LOADQ - PROBEQ; i < NQD; ++i) exp_quad(i);
-                // P buffer reuse: PV_{j-2} must have drained it.  Seeing S_{j+1} (issued after PV_{j-2}, in-order
-                // tensor pipe) proves that in every other step; the last one waits for PV_{j-1} explicitly.
-                if (j >= 2) mbar_wait(&bars->pv_done[t][(j - 1) & 1], ((j - 1) >> 1) & 1);
+                // P buffer reuse (two buffers): PV_{j-2} must have drained it.  Seeing S_{j+1} (issued after PV_{j-2},
+                // in-order tensor pipe) proves that in every other step; the last one waits for PV_{j-1} explicitly.
+                if constexpr (C::PBUFS == 2) {
+                    if (j >= 2) mbar_wait(&bars->pv_done[t][(j - 1) & 1], ((j - 1) >> 1) & 1);
+                }
             }
-            const uint32_t p_addr = p_base + (j & 1) * 32;
+            if constexpr (C::PBUFS == 1) {
+                // one P buffer: PV_{j-1} must have read P_{j-1} out of it.  It was published PUBQ quads into this
+                // step and the tensor pipe has had the whole step for it, so this wait is normally already satisfied.
+                if (j >= 1) {
+                    mbar_wait(&bars->pv_done[t][(j - 1) & 1], ((j - 1) >> 1) & 1);
+                    tc_fence_after();
+                }
+            }
+            const uint32_t p_addr = p_base + (C::PBUFS == 2 ? (j & 1) * 32 : 0);
             if constexpr (C::PMODE == QA_P_E4M3) {
                 tmem_st_words<CW / 4>(p_addr, pw);
             } else if constexpr (C::PMODE == QA_P_E4M3_HILO) {
@@ -816,6 +856,29 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             }
         }
 #endif
+        if constexpr (C::QTMEM) {
+            // this thread's query row -> tensor memory (lane = row, D bytes = D / 4 columns), straight from global
+            // memory: the A operand of every Q K^T MMA of the tile
+            if (hf == 0) {
+                const uint8_t* qrow = p.q + (long long)b * p.q_sb + (long long)h * p.q_sh +
+                                      (long long)min(row_g, p.Sq - 1) * p.q_sr;
+                const uint32_t q_addr = tmem + lane_base + C::TM_Q + t * 128;
+                constexpr int NW = (D / 4 < 32) ? D / 4 : 32;  // words per tcgen05.st
+#pragma unroll
+                for (int c0 = 0; c0 < D / 4; c0 += NW) {
+                    uint32_t w[NW];
+#pragma unroll
+                    for (int i = 0; i < NW; i += 4) {
+                        const uint4 v = __ldg(reinterpret_cast<const uint4*>(qrow + (c0 + i) * 4));
+                        w[i] = v.x, w[i + 1] = v.y, w[i + 2] = v.z, w[i + 3] = v.w;
+                    }
+                    tmem_st_words<NW>(q_addr + c0, w);
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(&bars->q_full[t]);
+            }
+        }
         float s_a[CW], s_b[CW];
         float mx;
         QA_STAMP(t, 78, 1);
@@ -974,6 +1037,8 @@ static int launch_cfg(const AttnArgs& a, cudaStream_t stream, int* launches) {
     p.scale_v = a.scale_v;
     p.lse = a.lse;
     p.out = a.out;
+    p.q = static_cast<const uint8_t*>(a.q8);
+    p.q_sb = a.qs[0] * C::QB, p.q_sh = a.qs[1] * C::QB, p.q_sr = a.qs[2] * C::QB;
     p.B = a.B, p.Hq = a.Hq, p.Hkv = a.Hkv, p.Sq = a.Sq, p.Skv = a.Skv;
     p.causal = a.causal;
     p.sm_scale_log2 = a.sm_scale * kLog2e;

@@ -9,6 +9,7 @@ import cutlass
 import torch
 
 path = os.path.join(os.path.dirname(flashinfer.__file__), "data", "cutlass", "examples", "python", "CuTeDSL", "blackwell", "fmha.py")
+sys.path.insert(0, os.path.dirname(path)); sys.path.insert(0, os.path.dirname(os.path.dirname(path)))
 spec = importlib.util.spec_from_file_location("cutedsl_fmha", path)
 mod = importlib.util.module_from_spec(spec)
 spec.loader.exec_module(mod)
