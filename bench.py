@@ -273,20 +273,32 @@ def seq_sharded_block(dev, rank, world, dist, steps, warmup):
     # time split (separate untimed pass: the marks are CUDA events on the calling stream at the phase boundaries)
     split = None
     if strategy == "gather":
+        # (calls issued back to back, the LAST one analysed: the host is then ahead of the GPU as in the timed loop)
         acc = {}
-        reps = 5
+        reps = 4
+        all_marks = []
+        barrier()
         for _ in range(reps):
             parallel.trace_marks = []
             parallel.ring_fp8_attention(*loc)
-            torch.cuda.synchronize()
-            marks, parallel.trace_marks = parallel.trace_marks, None
-            for (_, a), (lb, b) in zip(marks, marks[1:]):
-                acc[lb] = acc.get(lb, 0.0) + a.elapsed_time(b)
-        split = {("transfer_exposed" if k_ == "wait" else ("attention" if k_ == "attend" else k_)) + "_ms": v_ / reps
+            all_marks.append(parallel.trace_marks)
+            parallel.trace_marks = None
+        torch.cuda.synchronize()
+        marks = all_marks[-1]
+        prev_end = all_marks[-2][-1][1]
+        acc["gap_after_previous_call"] = prev_end.elapsed_time(marks[0][1])
+        waits = []
+        for (_, a), (lb, b) in zip(marks, marks[1:]):
+            acc[lb] = acc.get(lb, 0.0) + a.elapsed_time(b)
+            if lb == "wait":
+                waits.append(round(a.elapsed_time(b), 4))
+        split = {("transfer_exposed" if k_ == "wait" else ("attention" if k_ == "attend" else k_)) + "_ms": v_
                  for k_, v_ in acc.items()}
-        split["note"] = ("scales = amax pass + all_reduce(MAX); quant_kv / quant_q = quantise with the global scales (K/V "
-                         "first: they travel); transfer_exposed = time the compute stream waited for blocks; attention = "
-                         "the per-head-group launches")
+        split["transfer_exposed_per_head_group_ms"] = waits
+        split["note"] = ("one call of a back-to-back series, CUDA events on the compute stream: amax = local amax pass; scales = "
+                         "all_reduce(MAX) of the head scales; quant_kv / quant_q = quantise with the global scales (K/V first: "
+                         "they travel); transfer_exposed = time the compute stream waited for blocks; attention = the "
+                         "per-head-group launches")
 
     # the transfer alone, by the transport in use: every head group's blocks, nothing else running
     wire_bytes = (world - 1) * B * H * S_loc * D * (1 + v_item)  # received per rank per step
@@ -299,8 +311,9 @@ def seq_sharded_block(dev, rank, world, dist, steps, warmup):
                 barrier()
                 if rep == 1:
                     e0.record()
-                for ev in comm.pull(chunks):
-                    main.wait_event(ev)
+                for evs in comm.pull(chunks):
+                    for ev in evs:
+                        main.wait_event(ev)
         else:
             k_loc = torch.empty((B, H, S_loc, D), dtype=torch.uint8, device=dev)
             v_loc = torch.empty((B, H, S_loc, D * v_item), dtype=torch.uint8, device=dev)

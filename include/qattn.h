@@ -178,6 +178,10 @@ int qa_merge_partials(float* o_acc, float* lse_acc, const void* o_new, int o_dty
  * reference never shards a sequence).  Asynchronous on `stream`; launches no kernel. */
 int qa_copy_2d(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes, size_t rows,
                void* stream);
+/* n such copies in one call (copy i on streams[i]): a head group's blocks from every peer cost the host one crossing
+ * of the boundary instead of 2 x world. */
+int qa_copy_2d_batch(int n, void* const* dst, const size_t* dst_pitch, const void* const* src, const size_t* src_pitch,
+                     const size_t* width_bytes, const size_t* rows, void* const* streams);
 
 /* Number of kernels the previous call on this thread launched (for bench.py's gpu_launches accounting). */
 int qa_last_launch_count(void);

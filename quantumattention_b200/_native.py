@@ -31,6 +31,7 @@ EXPORTED_SYMBOLS = (
     "qa_attn_fwd",
     "qa_merge_partials",
     "qa_copy_2d",
+    "qa_copy_2d_batch",
     "qa_last_launch_count",
 )
 
@@ -100,6 +101,10 @@ def load(build_if_missing: bool = True):
         lib.qa_merge_partials.restype = ctypes.c_int
         lib.qa_copy_2d.argtypes = [vp, ctypes.c_size_t, vp, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, vp]
         lib.qa_copy_2d.restype = ctypes.c_int
+        szp = ctypes.POINTER(ctypes.c_size_t)
+        lib.qa_copy_2d_batch.argtypes = [ctypes.c_int, ctypes.POINTER(vp), szp, ctypes.POINTER(vp), szp, szp, szp,
+                                         ctypes.POINTER(vp)]
+        lib.qa_copy_2d_batch.restype = ctypes.c_int
         if lib.qa_abi_version() != ABI_VERSION:
             raise NativeError(f"ABI mismatch: library {lib.qa_abi_version()} != binding {ABI_VERSION}")
         _lib = lib
@@ -446,3 +451,19 @@ def merge_partials(o_acc: Optional[torch.Tensor], lse_acc: torch.Tensor, o_new: 
 def copy_2d(dst_ptr: int, dst_pitch: int, src_ptr: int, src_pitch: int, width_bytes: int, rows: int, stream: int) -> None:
     """Asynchronous strided block copy on the copy engines (``qa_copy_2d``); raw device addresses and a raw stream."""
     _check(load().qa_copy_2d(dst_ptr, dst_pitch, src_ptr, src_pitch, width_bytes, rows, stream), "qa_copy_2d")
+
+
+class CopyBatch:
+    """A fixed list of strided block copies (``qa_copy_2d_batch``) marshalled once and issued with one call."""
+
+    def __init__(self, copies):
+        """copies: sequence of (dst_ptr, dst_pitch, src_ptr, src_pitch, width_bytes, rows, raw_stream)."""
+        n = self.n = len(copies)
+        vp, sz = ctypes.c_void_p, ctypes.c_size_t
+        cols = list(zip(*copies)) if n else [[]] * 7
+        self.args = ((vp * n)(*cols[0]), (sz * n)(*cols[1]), (vp * n)(*cols[2]), (sz * n)(*cols[3]), (sz * n)(*cols[4]),
+                     (sz * n)(*cols[5]), (vp * n)(*cols[6]))
+
+    def issue(self) -> None:
+        a = self.args
+        _check(load().qa_copy_2d_batch(self.n, a[0], a[1], a[2], a[3], a[4], a[5], a[6]), "qa_copy_2d_batch")

@@ -305,6 +305,18 @@ int qa_copy_2d(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, s
     return QA_OK;
 }
 
+int qa_copy_2d_batch(int n, void* const* dst, const size_t* dst_pitch, const void* const* src, const size_t* src_pitch,
+                     const size_t* width_bytes, const size_t* rows, void* const* streams) {
+    g_launches = 0;
+    if (n < 0 || (n > 0 && (!dst || !dst_pitch || !src || !src_pitch || !width_bytes || !rows || !streams)))
+        return set_error(QA_ERR_INVALID, "null argument array");
+    for (int i = 0; i < n; ++i) {
+        int rc = qa_copy_2d(dst[i], dst_pitch[i], src[i], src_pitch[i], width_bytes[i], rows[i], streams[i]);
+        if (rc != QA_OK) return rc;
+    }
+    return QA_OK;
+}
+
 int qa_merge_partials(float* o_acc, float* lse_acc, const void* o_new, int o_dtype, const float* lse_new, void* out,
                       long long rows, int D, int first, void* stream) {
     g_launches = 0;

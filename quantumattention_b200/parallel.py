@@ -249,7 +249,10 @@ class PeerGather:
         self.buf = symm_mem.empty(2 * self.slot, dtype=torch.uint8, device=device)
         self.hdl = symm_mem.rendezvous(self.buf, pg)
         self.peers = [self.hdl.get_buffer(r, (2 * self.slot,), torch.uint8, 0) for r in range(self.world)]
-        self.stream = torch.cuda.Stream(device=device)
+        self.peer_ptrs = [t.data_ptr() for t in self.peers]
+        self.streams = [torch.cuda.Stream(device=device) for _ in range(int(os.environ.get("QA_PEER_STREAMS", "2")))]
+        self.batches = {}
+        self.cur = 0
         self.phase = 0
         B, H, S, D = k_shape
         self.k_all = torch.empty((B, H, self.world * S, D), dtype=torch.uint8, device=device)
@@ -262,32 +265,54 @@ class PeerGather:
         vb = self.buf[base + self.nk:base + self.nk + self.nv].view(tuple(v_shape[:-1]) + (v_shape[-1] * v_itemsize,))
         return kb, vb
 
-    def pull(self, chunks: Sequence[Tuple[int, int]]) -> List[torch.cuda.Event]:
-        """Barrier, then start the pulls for every head group; returns one event per group (its blocks have landed)."""
+    def start(self) -> None:
+        """Device-side barrier (every rank's blocks of this call are in its slot); the copy streams wait for it."""
         main = torch.cuda.current_stream(self.device)
-        self.hdl.barrier(channel=self.phase)  # every rank's blocks of this call are in its slot
-        self.stream.wait_stream(main)
-        raw = self.stream.cuda_stream
-        B, H, S_all, D = self.k_all.shape
-        S = S_all // self.world
-        Dv = self.v_all.shape[-1]
-        base = self.phase * self.slot
-        events = []
-        for lo, hi in chunks:
+        self.hdl.barrier(channel=self.phase)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        for st in self.streams:
+            st.wait_event(ready)
+        self.cur, self.phase = self.phase, self.phase ^ 1
+
+    def pull_group(self, lo: int, hi: int) -> List[torch.cuda.Event]:
+        """Start the pulls of heads [lo, hi) from every rank (own block: a local copy); returns the events to wait for.
+        The copies are dealt round-robin to a few streams so that transfers from different peers overlap; the argument
+        arrays of a (slot, head range) are marshalled once and re-issued with one call of the C ABI - the host cost of
+        issuing the copies is what the first head group's transfer hides behind, so it has to be small."""
+        key = (self.cur, lo, hi)
+        batch = self.batches.get(key)
+        if batch is None:
+            B, H, S_all, D = self.k_all.shape
+            S = S_all // self.world
+            Dv = self.v_all.shape[-1]
+            base = self.cur * self.slot
+            k_dst, v_dst = self.k_all.data_ptr(), self.v_all.data_ptr()
+            raws = [st.cuda_stream for st in self.streams]
+            copies, n = [], 0
             for i in range(self.world):
-                r = (self.rank + i) % self.world  # own block first (local copy), then the peers, each rank another order
-                src = self.peers[r].data_ptr() + base
+                r = (self.rank + i) % self.world  # own block first, then the peers - every rank in another order
+                src = self.peer_ptrs[r] + base
                 for b in range(B):
-                    # K: rows = heads of the group; a row is this rank-block of one head, S x D bytes
-                    _native.copy_2d(self.k_all.data_ptr() + ((b * H + lo) * S_all + r * S) * D, S_all * D,
-                                    src + (b * H + lo) * S * D, S * D, S * D, hi - lo, raw)
-                    _native.copy_2d(self.v_all.data_ptr() + ((b * H + lo) * S_all + r * S) * Dv, S_all * Dv,
-                                    src + self.nk + (b * H + lo) * S * Dv, S * Dv, S * Dv, hi - lo, raw)
+                    # rows = heads of the group; a row is this rank-block of one head: S x D bytes of K, S x Dv of V
+                    copies.append((k_dst + ((b * H + lo) * S_all + r * S) * D, S_all * D, src + (b * H + lo) * S * D,
+                                   S * D, S * D, hi - lo, raws[n % len(raws)]))
+                    copies.append((v_dst + ((b * H + lo) * S_all + r * S) * Dv, S_all * Dv,
+                                   src + self.nk + (b * H + lo) * S * Dv, S * Dv, S * Dv, hi - lo, raws[(n + 1) % len(raws)]))
+                    n += 2
+            batch = self.batches[key] = _native.CopyBatch(copies)
+        batch.issue()
+        evs = []
+        for st in self.streams:
             ev = torch.cuda.Event()
-            ev.record(self.stream)
-            events.append(ev)
-        self.phase ^= 1
-        return events
+            ev.record(st)
+            evs.append(ev)
+        return evs
+
+    def pull(self, chunks: Sequence[Tuple[int, int]]) -> List[List[torch.cuda.Event]]:
+        """start() + every head group at once (bench.py's transfer-alone probe)."""
+        self.start()
+        return [self.pull_group(lo, hi) for lo, hi in chunks]
 
 
 def ring_fp8_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: Optional[float] = None,
@@ -330,6 +355,8 @@ def ring_fp8_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, sca
     if q.is_cuda:
         _mark("start", q.device)
     scales = torch.stack(be.local_scales([q, k] if v16 else [q, k, v]))  # [2 or 3, B, H] fp32
+    if q.is_cuda:
+        _mark("amax", q.device)
     if world > 1:
         dist.all_reduce(scales, op=dist.ReduceOp.MAX, group=group)
     sq, sk, sv = scales[0], scales[1], (None if v16 else scales[2])
@@ -352,6 +379,7 @@ def ring_fp8_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, sca
             chunks = [(lo, min(H, lo + hc)) for lo in range(0, H, hc)]
         f8 = torch.float8_e4m3fn
         transport, comm = resolve_transport(transport, group, q, k, v, v.element_size() if v16 else 1)
+        main = torch.cuda.current_stream(q.device) if q.is_cuda else None
         if transport == "peer":
             kb, vb = comm.send_views(k.shape, v.shape, v.element_size() if v16 else 1)
             if v16:
@@ -359,10 +387,14 @@ def ring_fp8_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, sca
                 vb.view(v.dtype).copy_(v)
             else:
                 be.quantize([k, v], [sk, sv], outs=[kb, vb])
-            waits = comm.pull(chunks)
+            comm.start()
             k_all = comm.k_all.view(f8)
             v_all = comm.v_all.view(v.dtype if v16 else f8)
-            wait = lambda w: torch.cuda.current_stream(q.device).wait_event(w)
+            fetch = lambda lo, hi: comm.pull_group(lo, hi)
+
+            def wait(evs):
+                for ev in evs:
+                    main.wait_event(ev)
         else:
             if v16:
                 (k8,) = be.quantize([k], [sk])
@@ -371,16 +403,21 @@ def ring_fp8_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, sca
                 k8, v_send = be.quantize([k, v], [sk, sv])
             k_all = torch.empty((B, H, world * S, D), dtype=f8, device=q.device)
             v_all = torch.empty((B, H, world * S, D), dtype=v_send.dtype, device=q.device)
-            waits = [_nccl_gather_heads([k8, v_send], [k_all, v_all], lo, hi, group) for lo, hi in chunks]
+            fetch = lambda lo, hi: _nccl_gather_heads([k8, v_send], [k_all, v_all], lo, hi, group)
             wait = lambda w: w.wait()
+        # the first group's transfer is started at once; every later one right before the attention of the group in
+        # front of it is launched, so the host never spends more than one group's worth of issue time ahead of a launch
+        pending = fetch(*chunks[0])
         if q.is_cuda:
             _mark("quant_kv", q.device)
         (q8,) = be.quantize([q], [sq])
         if q.is_cuda:
             _mark("quant_q", q.device)
         # 3. one launch per head group over ALL keys, as its blocks land
-        for (lo, hi), w in zip(chunks, waits):
-            wait(w)
+        for i, (lo, hi) in enumerate(chunks):
+            nxt = fetch(*chunks[i + 1]) if i + 1 < len(chunks) else None
+            wait(pending)
+            pending = nxt
             if q.is_cuda:
                 _mark("wait", q.device)
             dst = out[:, lo:hi] if B == 1 else None  # (a head range of a [1,H,S,D] tensor is dense)
