@@ -103,6 +103,10 @@ constexpr float kLog2e = 1.4426950408889634f;
 #ifndef QA_QTMEM
 #define QA_QTMEM 1     // e4m3 Q in tensor memory, Q K^T as a TS-form MMA: 1 = where it pays (D = 256), 2 = everywhere, 0 = nowhere
 #endif
+#ifndef QA_SYNCCHECK
+#define QA_SYNCCHECK 0  // 1: the softmax threads wait for EVERY PV_{j-1} (compute-sanitizer synccheck flags barrier phases nobody
+                        // observed; the shipping kernel only waits for a PV where its completion matters - rescale, last step)
+#endif
 #ifndef QA_FORCE_PBUFS1
 #define QA_FORCE_PBUFS1 0  // experiment: one P buffer without Q in TMEM (measured: C2 172.4 -> 180.6 us)
 #endif
@@ -822,6 +826,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 if constexpr (C::PBUFS == 2) {
                     if (j >= 2) mbar_wait(&bars->pv_done[t][(j - 1) & 1], ((j - 1) >> 1) & 1);
                 }
+            }
+            if constexpr (QA_SYNCCHECK != 0 && C::PBUFS == 2) {
+                if (j >= 1 && !last) mbar_wait(&bars->pv_done[t][(j - 1) & 1], ((j - 1) >> 1) & 1);
             }
             if constexpr (C::PBUFS == 1) {
                 // one P buffer: PV_{j-1} must have read P_{j-1} out of it.  It was published PUBQ quads into this
