@@ -16,6 +16,7 @@ from . import build as _build
 
 QA_DT_BF16, QA_DT_FP16, QA_DT_E4M3 = 0, 1, 2
 QA_SCALE_HEAD, QA_SCALE_TOKEN, QA_SCALE_HEAD_TWO_PASS, QA_SCALE_HEAD_AMAX_ONLY, QA_SCALE_HEAD_GIVEN = 0, 1, 2, 3, 4
+QA_SCALE_HEAD_RELOAD = 5
 QA_WS_PERSISTENT = 0x100  # qa_quantize_fp8: the workspace was zeroed once and is reused (include/qattn.h)
 QA_P_E4M3, QA_P_E4M3_HILO, QA_P_16BIT = 0, 1, 2
 ABI_VERSION = 5
@@ -250,7 +251,7 @@ def quantize_fp8(tensors: Sequence[torch.Tensor], scale_mode: int,
                 raise ValueError("quantize_fp8: QA_SCALE_HEAD_GIVEN needs one [B,H] fp32 scale tensor per input")
             scales = [s_.to(device=dev, dtype=torch.float32).reshape(B, H).contiguous() for s_ in scales]
             ws, ws_ptr = None, None
-        elif scale_mode in (QA_SCALE_HEAD, QA_SCALE_HEAD_TWO_PASS, QA_SCALE_HEAD_AMAX_ONLY):
+        elif scale_mode in (QA_SCALE_HEAD, QA_SCALE_HEAD_TWO_PASS, QA_SCALE_HEAD_AMAX_ONLY, QA_SCALE_HEAD_RELOAD):
             scales = [torch.empty((B, H), dtype=torch.float32, device=dev) for _ in xs]
             n_ws = int(lib.qa_quantize_workspace_floats(B, H, max(t.shape[2] for t in xs), D))
             ws, flags = _workspace_for_call(idx, n_ws, workspace)
