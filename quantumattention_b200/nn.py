@@ -22,6 +22,13 @@ from . import _native, config, ops
 
 _SUPPORTED_HEAD_DIMS = (64, 128, 256)
 _SCALING_METHODS = ("head-wise", "token-wise")
+_F16_OR_E4M3 = (torch.float16, torch.bfloat16, torch.float8_e4m3fn)
+
+
+def _plain_tensor(x) -> bool:
+    """A real tensor for sure (exact type, no functional wrapper): the common eager case, decided without the
+    isinstance chain of ``is_fake``."""
+    return type(x) is torch.Tensor and not torch._is_functional_tensor(x)
 
 
 # ------------------------------------------------------------------------------------------------ quantiser
@@ -112,8 +119,10 @@ def _pre_check(device: torch.device) -> Tuple[bool, str]:
 
 def _validate_input(query, key, value, attn_mask=None, dropout_p=0.0, is_causal=False, scale=None,
                     scaling_method=None, scale_q=None, scale_k=None, scale_v=None) -> Tuple[bool, str]:
-    if any(t.requires_grad for t in (query, key, value)):
+    # (the eager hot path runs through here on every call: attributes are fetched once)
+    if query.requires_grad or key.requires_grad or value.requires_grad:
         return False, "NYI: query, key, and value must be leaf tensors"
+    qdt, kdt, vdt = query.dtype, key.dtype, value.dtype
     if attn_mask is not None:
         return False, "NYI: attn_mask must be None"
     if dropout_p != 0.0:
@@ -122,12 +131,12 @@ def _validate_input(query, key, value, attn_mask=None, dropout_p=0.0, is_causal=
         return False, "scale must be positive"
     f16 = (torch.float16, torch.bfloat16)
     if scaling_method is None:
-        if query.dtype != key.dtype or query.dtype != value.dtype:
+        if qdt != kdt or qdt != vdt:
             return False, (
                 "Expected query, key, and value to have the same dtype, but got "
                 f"query.dtype: {query.dtype}, key.dtype: {key.dtype}, and value.dtype: {value.dtype} instead."
             )
-        if query.dtype not in f16:
+        if qdt not in f16:
             return False, (
                 "Expected query, key, and value to have dtype torch.float16 or torch.bfloat16, "
                 f"but got query.dtype: {query.dtype} instead."
@@ -135,60 +144,62 @@ def _validate_input(query, key, value, attn_mask=None, dropout_p=0.0, is_causal=
     else:
         if scaling_method not in _SCALING_METHODS:
             return False, f"Unsupported scaling_method: {scaling_method}"
-        if query.dtype not in f16 + (torch.float8_e4m3fn,):
+        if qdt not in _F16_OR_E4M3:
             return False, (
                 "Expected query to have dtype torch.float16, torch.bfloat16, or torch.float8_e4m3fn, "
                 f"but got query.dtype: {query.dtype} instead."
             )
         # a tensor is pre-quantised exactly when its scale comes with it (16-bit q/k WITH scales is undefined in the
         # reference); the key alone may be pre-quantised (K8 reuse: the query is quantised here)
-        if (query.dtype == torch.float8_e4m3fn) != (scale_q is not None) or \
-                (key.dtype == torch.float8_e4m3fn) != (scale_k is not None):
+        if (qdt == torch.float8_e4m3fn) != (scale_q is not None) or \
+                (kdt == torch.float8_e4m3fn) != (scale_k is not None):
             return False, "float8_e4m3fn query/key need scale_q and scale_k, and 16-bit query/key must not pass them"
         if scale_q is not None and scale_k is None:
             return False, "a pre-quantised query needs a pre-quantised key (scale_q and scale_k)"
-        if key.dtype not in f16 + (torch.float8_e4m3fn,):
+        if kdt not in _F16_OR_E4M3:
             return False, (
                 "Expected key to have dtype torch.float16, torch.bfloat16, or torch.float8_e4m3fn, "
                 f"but got key.dtype: {key.dtype} instead."
             )
-        if (value.dtype == torch.float8_e4m3fn) != (scale_v is not None):
+        if (vdt == torch.float8_e4m3fn) != (scale_v is not None):
             return False, "a float8_e4m3fn value needs scale_v, and a 16-bit value must not pass it"
-    if query.dtype != key.dtype and not (scaling_method is not None and key.dtype == torch.float8_e4m3fn):
+    if qdt != kdt and not (scaling_method is not None and kdt == torch.float8_e4m3fn):
         return False, (
             "Expected query and key to have the same dtype, but got "
             f"query.dtype: {query.dtype}, key.dtype: {key.dtype} instead."
         )
-    if value.dtype not in f16 and not (scaling_method is not None and scale_v is not None):
+    if vdt not in f16 and not (scaling_method is not None and scale_v is not None):
         return False, (
             f"Expected value to have dtype torch.float16 or torch.bfloat16, but got value.dtype: {value.dtype} instead."
         )
-    if query.device != key.device or query.device != value.device:
+    qdev = query.device
+    if qdev != key.device or qdev != value.device:
         return False, (
             "Expected query, key, and value to have the same device type, but got "
             f"query.device: {query.device}, key.device: {key.device}, and value.device: {value.device} instead."
         )
-    if query.device.type != "cuda":
+    if qdev.type != "cuda":
         return False, "Expected query, key, and value to be on a CUDA device"
-    if query.dim() != 4 or key.dim() != 4 or value.dim() != 4:
+    qs, ks, vs = query.shape, key.shape, value.shape
+    if len(qs) != 4 or len(ks) != 4 or len(vs) != 4:
         return False, "NYI: query, key, and value must be 4D tensors"
-    if key.size(-2) != value.size(-2):
+    if ks[2] != vs[2]:
         return False, (
             "Expect key and value to have the same sequence length "
-            f"but got Sk={key.size(-2)} and Sv={value.size(-2)}."
+            f"but got Sk={ks[2]} and Sv={vs[2]}."
         )
-    if value.size(-1) != query.size(-1) or key.size(-1) != query.size(-1):
+    if vs[3] != qs[3] or ks[3] != qs[3]:
         return False, "NYI: query, key and value must have the same embedding dimension"
-    if query.size(0) != key.size(0) or key.size(-3) != value.size(-3) or key.size(0) != value.size(0):
+    if qs[0] != ks[0] or ks[1] != vs[1] or ks[0] != vs[0]:
         return False, "Expect query, key and value to agree on batch size, and key/value on the number of heads."
-    if query.size(-3) % key.size(-3) != 0:
+    if qs[1] % ks[1] != 0:
         return False, (
             "Expect the number of query heads to be a multiple of key/value heads "
-            f"but got Hq={query.size(-3)} and Hkv={key.size(-3)}."
+            f"but got Hq={qs[1]} and Hkv={ks[1]}."
         )
-    if query.size(-1) not in _SUPPORTED_HEAD_DIMS:
-        return False, f"Unsupported head dimension: {query.size(-1)}"
-    if query.size(-2) < 1 or key.size(-2) < 1:
+    if qs[3] not in _SUPPORTED_HEAD_DIMS:
+        return False, f"Unsupported head dimension: {qs[3]}"
+    if qs[2] < 1 or ks[2] < 1:
         return False, "Empty sequences are not supported"
     return True, ""
 
@@ -272,8 +283,12 @@ def fp8_attention(query, key, value, attn_mask=None, dropout_p=0.0, is_causal=Fa
         raise ValueError(reason)
     from torch._subclasses.fake_tensor import is_fake
 
-    traced = torch.compiler.is_dynamo_compiling() or any(
-        is_fake(x) for x in (query, key, value, scale_q, scale_k) if x is not None)
+    if torch.compiler.is_dynamo_compiling():
+        traced = True
+    elif _plain_tensor(query) and _plain_tensor(key) and _plain_tensor(value) and scale_q is None and scale_k is None:
+        traced = False
+    else:
+        traced = any(is_fake(x) for x in (query, key, value, scale_q, scale_k) if x is not None)
     if not traced and not config.attention.force_eager_fallback:
         return _fp8_attention_direct(query, key, value, is_causal, scale, scale_q, scale_k, scaling_method, scale_v)
     if scale_v is not None:
@@ -300,7 +315,9 @@ def attention(query, key, value, attn_mask=None, dropout_p=0.0, is_causal=False,
         raise ValueError(f"Unsupported input: {reason}")
     from torch._subclasses.fake_tensor import is_fake
 
-    traced = torch.compiler.is_dynamo_compiling() or any(is_fake(x) for x in (query, key, value))
+    traced = torch.compiler.is_dynamo_compiling() or not (
+        _plain_tensor(query) and _plain_tensor(key) and _plain_tensor(value)) and any(
+        is_fake(x) for x in (query, key, value))
     if not traced and not config.attention.force_eager_fallback:
         return ops.attention_native(query, key, value, is_causal=is_causal, scale=scale)  # no dispatcher hop
     return torch.ops.quantum_attn.attention_forward(

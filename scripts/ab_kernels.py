@@ -12,7 +12,7 @@ shapes = [("C2", 24, 4608, 128, False), ("C3", 32, 8192, 128, True), ("d64", 32,
 only = os.environ.get("AB_SHAPES")
 if only:
     shapes = [s for s in shapes if s[0] in only.split(",")]
-modes = os.environ.get("AB_MODES", "16bit,fp8").split(",")
+modes = os.environ.get("AB_MODES", "16bit,fp8,hilo").split(",")
 out = []
 for name, H, S, D, causal in shapes:
     sets = []
