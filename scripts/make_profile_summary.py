@@ -37,7 +37,7 @@ for name in ("attn", "quant"):
             def tobytes(v, unit):
                 v = float(v.replace(",", "")); return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[unit]
             tb = tobytes(d["dram__bytes_read.sum"], u["dram__bytes_read.sum"]) + tobytes(d["dram__bytes_write.sum"], u["dram__bytes_write.sum"])
-            traffic[kn.split("<")[0].split("::")[-1] + ("" if name == "attn" else "")] = tb
+            traffic[kn.split("<")[0].split("::")[-1].replace("void ", "").strip()] = tb
 open(os.path.join(P, f"{R}_ncu_summary.md"), "w").write("\n".join(lines))
 
 # launch list -> per-kernel table + the raw csv
