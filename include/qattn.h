@@ -90,8 +90,9 @@ int qa_device_supported(int dev);
  *   amax_ws     scratch of qa_quantize_workspace_floats(B, H, max_i S[i], D) floats, 8-byte aligned (head-wise only;
  *               may be NULL for token mode); need not be zeroed (but see QA_WS_PERSISTENT), must not be shared by
  *               calls that can run concurrently.  The single-pass head-wise kernel (one CTA per SM, CTAs rendezvous
- *               through this workspace) needs its whole grid resident at once: if another kernel holds the SMs for
- *               seconds the launch traps (bounded poll) rather than hangs - serialise such calls per device.
+ *               through this workspace) needs its whole grid resident at once: it is launched with the cooperative
+ *               attribute, so it is only scheduled once the grid fits (concurrent calls on other streams queue), and
+ *               a bounded poll turns any remaining non-resident grid into a trap rather than a hang.
  */
 size_t qa_quantize_workspace_floats(int B, int H, int max_S, int D);
 int qa_quantize_fp8(int n_tensors, const void* const* x, int x_dtype, const int64_t* x_strides, void* const* x8,

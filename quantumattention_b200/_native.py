@@ -134,6 +134,7 @@ def last_launch_count() -> int:
     return int(load().qa_last_launch_count())
 
 
+_ws_floats = {}  # (B, H, S, D) -> qa_quantize_workspace_floats(...)
 _ws_cache = {}  # (device index, raw stream handle) -> fp32 workspace, zero-filled when allocated, reused by every call
 _I64x3 = ctypes.c_int64 * 3
 _nullctx = contextlib.nullcontext()
@@ -367,7 +368,10 @@ def fp8_attn_func(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale_mo
         lse = torch.empty((B, Hq, Sq), dtype=torch.float32, device=dev) if return_lse else None
         ws_ptr, flags = None, 0
         if not token or v_fp8:
-            n_ws = int(lib.qa_quantize_workspace_floats(B, max(Hq, Hkv), max(Sq, Skv), D))
+            wkey = (B, max(Hq, Hkv), max(Sq, Skv), D)
+            n_ws = _ws_floats.get(wkey)
+            if n_ws is None:
+                n_ws = _ws_floats[wkey] = int(lib.qa_quantize_workspace_floats(*wkey))
             ws, flags = _workspace_for_call(idx, n_ws, None)
             ws_ptr = ws.data_ptr()
         base = buf.data_ptr()

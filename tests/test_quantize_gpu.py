@@ -238,3 +238,23 @@ def test_plain_scratch_workspace_full_of_garbage():
         (x8,), (scale,) = _native.quantize_fp8([x.cuda()], _native.QA_SCALE_HEAD, workspace=ws)
         b, s = oracle.quantize_fp8(x.float().numpy(), "head-wise")
         assert np.array_equal(x8.view(torch.uint8).cpu().numpy(), b) and np.array_equal(scale.cpu().numpy(), s)
+
+
+def test_two_streams_quantise_concurrently_without_deadlock():
+    """The single-pass kernel's CTAs wait for each other (one CTA per SM): two such grids on different streams must
+    not split the SMs between them and spin forever.  They are launched cooperatively - a grid is scheduled only once
+    it fits as a whole - so concurrent calls queue; results stay byte-exact.  (Each stream has its own workspace.)"""
+    g = torch.Generator().manual_seed(21)
+    xs = [torch.randn(1, 24, 4608, 128, generator=g).to(torch.bfloat16).cuda() for _ in range(2)]
+    refs = [oracle.quantize_fp8(x.float().cpu().numpy(), "head-wise") for x in xs]
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    torch.cuda.synchronize()
+    outs = [None, None]
+    for rep in range(25):
+        for i, st in enumerate(streams):
+            with torch.cuda.stream(st):
+                outs[i] = _native.quantize_fp8([xs[i]], _native.QA_SCALE_HEAD)
+    torch.cuda.synchronize()
+    for i in range(2):
+        (x8,), (sc,) = outs[i]
+        assert np.array_equal(sc.cpu().numpy(), refs[i][1]) and np.array_equal(x8.view(torch.uint8).cpu().numpy(), refs[i][0])
