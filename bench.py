@@ -435,7 +435,7 @@ def bind_to_gpu_numa_node(local_rank):
     return info
 
 
-def external_bars(sets, causal, fl, dev):
+def external_bars(sets, causal, fl, dev, workload=None):
     """On-box comparators, rank 0, untimed extras: none of these is the reference, and none
     computes the reference's FP8 function - they are the bf16 / fp16 attention kernels of the stock libraries on the
     same shape, for scale.  Kernel-only, CUDA events, 10 launches after 3 warm-ups, rotating inputs."""
@@ -504,9 +504,22 @@ def external_bars(sets, causal, fl, dev):
         del bshd
     except Exception as e:
         res["flashinfer_single_prefill_bf16"] = "unavailable: " + repr(e)[:100]
+    # NVIDIA's CuTe-DSL Blackwell FMHA example (shipped inside the flashinfer wheel), FP8 and fp16 inputs, in a process of
+    # its own (it JIT-compiles; ~10 s per variant) - a comparator, not the reference and not product code
+    if workload in ("C2_flux", "C3_llama"):
+        try:
+            import subprocess
+            out_ = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "cutedsl_fmha_bar.py"), workload],
+                                  capture_output=True, text=True, timeout=180).stdout
+            line_ = [ln for ln in out_.splitlines() if ln.startswith("CUTEDSL_JSON ")][-1]
+            for k_, v_ in json.loads(line_[len("CUTEDSL_JSON "):]).items():
+                res["cutedsl_fmha_" + k_.split("_", 2)[-1].lower()] = v_.get("tflops", "unavailable: " + str(v_.get("error")))
+        except Exception as e:
+            res["cutedsl_fmha"] = "unavailable: " + repr(e)[:100]
     res["unit"] = UNIT
-    res["note"] = ("stock bf16 attention kernels on the same shape and FLOP count (kernel only); the CuTe-DSL Blackwell FMHA "
-                   "with Float8E4M3FN inputs is measured by scripts/cutedsl_fmha_bar.sh when its JIT works offline")
+    res["note"] = ("stock attention kernels on the same shape and FLOP count, kernel only: bf16 cuDNN / flash / flash_attn / "
+                   "flashinfer, and NVIDIA's CuTe-DSL Blackwell FMHA example with Float8E4M3FN and Float16 inputs (its own "
+                   "benchmark loop); none of them computes the reference's mixed FP8 / 16-bit function")
     return res
 
 
@@ -839,7 +852,7 @@ def main():
     comparators = None
     if rank == 0 and world == 1 and not args.no_comparators and S <= 16384:
         try:
-            comparators = external_bars(sets, causal, fl, dev)
+            comparators = external_bars(sets, causal, fl, dev, args.workload)
         except Exception as e:
             comparators = {"error": repr(e)[:200]}
 
