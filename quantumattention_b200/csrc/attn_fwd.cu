@@ -17,12 +17,12 @@ static int launch_flags(const AttnArgs& a, cudaStream_t stream, int* launches) {
     return token ? launch_cfg<C, false, true>(a, stream, launches) : launch_cfg<C, false, false>(a, stream, launches);
 }
 
-template <int PMODE>
+template <int PMODE, bool PF16 = false>
 static int launch_d(const AttnArgs& a, cudaStream_t stream, int* launches) {
     switch (a.D) {
-        case 64: return launch_flags<AttnCfg<64, PMODE>>(a, stream, launches);
-        case 128: return launch_flags<AttnCfg<128, PMODE>>(a, stream, launches);
-        case 256: return launch_flags<AttnCfg<256, PMODE>>(a, stream, launches);
+        case 64: return launch_flags<AttnCfg<64, PMODE, false, PF16>>(a, stream, launches);
+        case 128: return launch_flags<AttnCfg<128, PMODE, false, PF16>>(a, stream, launches);
+        case 256: return launch_flags<AttnCfg<256, PMODE, false, PF16>>(a, stream, launches);
     }
     return set_error(QA_ERR_INVALID, "Unsupported head dimension: %d", a.D);
 }
@@ -42,7 +42,9 @@ int attn_fwd_dispatch(const AttnArgs& a, cudaStream_t stream, int* launches) {
     switch (a.p_mode) {
         case QA_P_E4M3: return launch_d<QA_P_E4M3>(a, stream, launches);
         case QA_P_E4M3_HILO: return launch_d<QA_P_E4M3_HILO>(a, stream, launches);
-        case QA_P_16BIT: return launch_d<QA_P_16BIT>(a, stream, launches);
+        case QA_P_16BIT:  // (P takes V's 16-bit type: a compile-time property of the kernel)
+            return a.out_dtype == QA_DT_FP16 ? launch_d<QA_P_16BIT, true>(a, stream, launches)
+                                             : launch_d<QA_P_16BIT, false>(a, stream, launches);
     }
     return set_error(QA_ERR_INVALID, "unknown p_mode %d", a.p_mode);
 #endif

@@ -4,10 +4,15 @@
 
 namespace qa {
 
+template <int D, bool PF16>
+static int launch16t(const AttnArgs& a, cudaStream_t stream, int* launches) {
+    using C = AttnCfg<D, QA_P_16BIT, true, PF16>;
+    return a.causal ? launch_cfg<C, true, false>(a, stream, launches) : launch_cfg<C, false, false>(a, stream, launches);
+}
 template <int D>
 static int launch16(const AttnArgs& a, cudaStream_t stream, int* launches) {
-    using C = AttnCfg<D, QA_P_16BIT, true>;
-    return a.causal ? launch_cfg<C, true, false>(a, stream, launches) : launch_cfg<C, false, false>(a, stream, launches);
+    // (P takes V's 16-bit type: a compile-time property of the kernel)
+    return a.out_dtype == QA_DT_FP16 ? launch16t<D, true>(a, stream, launches) : launch16t<D, false>(a, stream, launches);
 }
 
 int attn16_fwd_dispatch(const AttnArgs& a, cudaStream_t stream, int* launches) {

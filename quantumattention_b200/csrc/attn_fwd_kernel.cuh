@@ -116,11 +116,15 @@ constexpr float kLog2e = 1.4426950408889634f;
 
 // QK16_: Q and K stay 16-bit (bf16 / fp16) and QK^T runs as kind::f16 - the reference's `attn_func` path
 // (src/quantum_attn/tk/attention.py:238-240,289-313); it implies the 16-bit P mode and has no dequantisation scales.
-template <int D_, int PMODE_, bool QK16_ = false>
+// PF16_: the 16-bit type of P (= V = out) in the 16-bit P mode is fp16 (else bf16).  A compile-time choice: selected at run
+// time, the compiler converts every pair of probabilities to BOTH formats and picks one (64 extra F2FP per two steps
+// and thread in the round-2 stall table: 9 % of the softmax loop's instructions).
+template <int D_, int PMODE_, bool QK16_ = false, bool PF16_ = false>
 struct AttnCfg {
     static constexpr int D = D_;
     static constexpr int PMODE = PMODE_;
     static constexpr bool QK16 = QK16_;
+    static constexpr bool PF16 = PF16_;
     static constexpr bool V16 = (PMODE_ == QA_P_16BIT);
     static_assert(!QK16_ || V16, "16-bit Q/K go with 16-bit P and V");
     // Two shapes of CTA.  PAIR: two query tiles share the K / V tiles of one CTA (one CTA per SM, all 512 TMEM columns).
@@ -448,7 +452,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             const uint32_t qk_fmt = (C::QK16 && !p.qk_fp16) ? 1u : 0u;  // f16: 0 = fp16, 1 = bf16;  f8f6f4: 0 = e4m3
             const uint32_t idesc_qk = make_idesc(qk_fmt, qk_fmt, 0, 0, BM, BS);
             constexpr uint32_t idesc_pv8 = make_idesc(0, 0, 0, 1, BM, D);
-            const uint32_t idesc_pv = C::V16 ? make_idesc(p.out_fp16 ? 0 : 1, p.out_fp16 ? 0 : 1, 0, 1, BM, D) : idesc_pv8;
+            const uint32_t idesc_pv = C::V16 ? make_idesc(C::PF16 ? 0 : 1, C::PF16 ? 0 : 1, 0, 1, BM, D) : idesc_pv8;
             constexpr uint64_t qk_swz = (C::QK_ROW == 128) ? kSwz128 : kSwz64;
             constexpr uint64_t v_swz = (C::V_ROW == 128) ? kSwz128 : kSwz64;
             const uint64_t q_desc = make_smem_desc(smem_u32(smem + C::SMEM_Q + t * C::Q_TILE), 16, 8 * C::QK_ROW, qk_swz);
@@ -752,8 +756,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     pw[i] = h01 | (h23 << 16);
                     pw_lo[i] = pack_e4m3x4(p01.x - f01.x, p01.y - f01.y, p23.x - f23.x, p23.y - f23.y);
                 } else {
-                    pw[2 * i] = p.out_fp16 ? pack_f16x2(p01.x, p01.y) : pack_bf16x2(p01.x, p01.y);
-                    pw[2 * i + 1] = p.out_fp16 ? pack_f16x2(p23.x, p23.y) : pack_bf16x2(p23.x, p23.y);
+                    pw[2 * i] = C::PF16 ? pack_f16x2(p01.x, p01.y) : pack_bf16x2(p01.x, p01.y);
+                    pw[2 * i + 1] = C::PF16 ? pack_f16x2(p23.x, p23.y) : pack_bf16x2(p23.x, p23.y);
                 }
             };
 
