@@ -9,22 +9,26 @@ dev = torch.device("cuda:0")
 PM = {"fp8": 0, "hilo": 1, "16bit": 2}
 shapes = [("C2", 24, 4608, 128, False), ("C3", 32, 8192, 128, True), ("d64", 32, 8192, 64, False), ("d64c", 32, 8192, 64, True),
           ("d256", 16, 8192, 256, False), ("d256c", 16, 8192, 256, True), ("c4s", 4, 75600, 128, False)]
+modes = os.environ.get("AB_MODES", "16bit,fp8,hilo").split(",")
 only = os.environ.get("AB_SHAPES")
 if only:
     shapes = [s for s in shapes if s[0] in only.split(",")]
-modes = os.environ.get("AB_MODES", "16bit,fp8,hilo").split(",")
 out = []
 for name, H, S, D, causal in shapes:
     sets = []
     for i in range(3):
         q, k, v = (torch.randn((1, H, S, D), device=dev, dtype=torch.bfloat16) for _ in range(3))
         (q8, k8, v8), (sq, sk, sv) = _native.quantize_fp8([q, k, v], _native.QA_SCALE_HEAD)
-        sets.append((q8, k8, v, v8, sq, sk, sv))
+        (q8t, k8t), (sqt, skt) = _native.quantize_fp8([q, k], _native.QA_SCALE_TOKEN) if "token" in modes else ((None, None), (None, None))
+        sets.append((q8, k8, v, v8, sq, sk, sv, q8t, k8t, sqt, skt))
         del q, k
     fl = 4.0 * H * S * S * D / (2 if causal else 1)
     for mode in modes:
         def call(i):
-            q8, k8, v, v8, sq, sk, sv = sets[i % 3]
+            q8, k8, v, v8, sq, sk, sv, q8t, k8t, sqt, skt = sets[i % 3]
+            if mode == "token":  # per-token scales, default P mode
+                return _native.fp8_attn_fwd(q8t, k8t, v, sqt, skt, None, scale_mode=1, is_causal=causal, sm_scale=1 / math.sqrt(D),
+                                            p_mode=2, out_dtype=torch.bfloat16)
             if mode == "16bit":
                 return _native.fp8_attn_fwd(q8, k8, v, sq, sk, None, scale_mode=0, is_causal=causal, sm_scale=1 / math.sqrt(D),
                                             p_mode=2, out_dtype=torch.bfloat16)

@@ -16,6 +16,8 @@ timeout 300 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/b
 timeout 600 python scripts/ab_kernels.py $R > gpurun_out/kernels_$R.txt 2>&1
 timeout 300 python scripts/quant_time.py > gpurun_out/quant_time_$R.txt 2>&1
 timeout 400 python scripts/cutedsl_fmha_bar.py > gpurun_out/cutedsl_$R.log 2>&1
+for tool in memcheck racecheck; do timeout 900 compute-sanitizer --tool $tool --print-limit 20 python scripts/sanitize_small.py > gpurun_out/sanitizer_${tool}_$R.txt 2>&1; done
+QA_NATIVE_LIB=$PWD/quantumattention_b200/libqattn_sm100_synccheck.so timeout 900 compute-sanitizer --tool synccheck --print-limit 20 python scripts/sanitize_small.py > gpurun_out/sanitizer_synccheck_$R.txt 2>&1
 timeout 900 python scripts/sweep.py > gpurun_out/sweep_$R.md 2> gpurun_out/sweep_$R.err
 BENCH="python bench.py --steps 8 --warmup 3 --no-cpu-baseline --e2e-steps 1 --no-comparators --no-other-modes"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 12 -c 40 --csv --log-file gpurun_out/launches_$R.csv $BENCH > gpurun_out/ncu_list_$R.log 2>&1
