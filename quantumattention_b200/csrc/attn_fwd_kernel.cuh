@@ -110,6 +110,17 @@ constexpr float kLog2e = 1.4426950408889634f;
 #ifndef QA_FORCE_PBUFS1
 #define QA_FORCE_PBUFS1 0  // experiment: one P buffer without Q in TMEM (measured: C2 172.4 -> 180.6 us)
 #endif
+// Developer ablations (WRONG results, timing only; scripts/gpu_r02_abl.sh): issue only a part of the MMAs / evaluate only a
+// part of the exponentials, to measure how the step time responds to each resource.
+#ifndef QA_ABL_QK
+#define QA_ABL_QK 0    // > 0: Q K^T issues only this many of its K slices
+#endif
+#ifndef QA_ABL_PV
+#define QA_ABL_PV 0    // > 0: P V issues only this many of its MMAs per step
+#endif
+#ifndef QA_ABL_EXP
+#define QA_ABL_EXP 0   // > 0: only the first this-many pairs (of 32) of a step's scores go through scale + exp2
+#endif
 #ifndef QA_SPLIT
 #define QA_SPLIT 0     // 1: TWO softmax threads per query row (each owns half of a step's 64 columns): 4 softmax warps per scheduler
 #endif
@@ -195,7 +206,11 @@ struct AttnCfg {
     static constexpr int SMEM_BAR = SMEM_ONES + ONES_BYTES;
     static constexpr int SMEM_XCHG = SMEM_BAR + 512;          // split softmax: one float per (tile, share, row)
     static constexpr int XCHG_BYTES = (NH == 2) ? NQ * 2 * 128 * 4 : 0;
-    static constexpr int SMEM_TOTAL = SMEM_XCHG + XCHG_BYTES + 1024;  // + barriers + alignment slack
+    // per-token K scales (token-wise kernels): the 128 scales of a K / V tile ride the V ring - one 512-byte bulk copy
+    // per tile next to the V boxes, completing on the same barrier - and the softmax threads read them from shared memory
+    static constexpr int SMEM_SK = SMEM_XCHG + XCHG_BYTES;
+    static constexpr int SK_BYTES = STAGES * BN * 4;
+    static constexpr int SMEM_TOTAL = SMEM_SK + SK_BYTES + 1024;  // + barriers + alignment slack
     static_assert(SMEM_TOTAL * CTAS_PER_SM + 1024 * CTAS_PER_SM <= 233472, "shared memory budget exceeded");
     static constexpr int NSOFT = NQ * 4 * NH;           // softmax warps
     static constexpr int NTHREADS = (NSOFT + 4) * 32;   // softmax warpgroups + one warpgroup holding the MMA / TMA warps
@@ -240,6 +255,7 @@ struct AttnParams {
     float sm_scale_log2;  // sm_scale * log2(e)
     int out_fp16;
     int qk_fp16;  // QK16 configs: element type of Q and K
+    int sk_bulk;  // token-wise: rows of scale_k are 16-byte aligned -> staged through shared memory by bulk copies
     float inv_group;  // Hkv / Hq
     long long* trace;  // developer builds (-DQA_TRACE): per-step clock64 stamps of one CTA, else unused
     int trace_x, trace_y;
@@ -372,7 +388,30 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     };
     auto load_v = [&](int n) {
         const int s = n % C::STAGES;
-        mbar_arrive_expect_tx(&bars->v_full[s], C::V_TILE);
+        if constexpr (TOKEN) {
+            if (p.sk_bulk) {  // the tile's per-token K scales land with its V boxes (a ragged tail copies what exists)
+                const uint32_t sk_bytes = uint32_t(min(BN, p.Skv - n * BN)) * 4u;
+                mbar_arrive_expect_tx(&bars->v_full[s], C::V_TILE + sk_bytes);
+                bulk_load_1d(smem + C::SMEM_SK + s * (BN * 4), p.scale_k + size_t(bhkv) * p.Skv + size_t(n) * BN, sk_bytes,
+                             &bars->v_full[s], kEvictLast);
+            } else {
+                // rows of scale_k not 16-byte aligned (Skv % 4 != 0): no bulk copy - this lane moves the 128 scales itself
+                // and arrives a second time (the barrier then counts two arrivals per phase)
+                mbar_arrive_expect_tx(&bars->v_full[s], C::V_TILE);
+                const float* src = p.scale_k + size_t(bhkv) * p.Skv;
+                float* dst = reinterpret_cast<float*>(smem + C::SMEM_SK + s * (BN * 4));
+#pragma unroll 4
+                for (int i = 0; i < BN; i += 4) {
+                    float a[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) a[u] = __ldg(src + min(n * BN + i + u, p.Skv - 1));
+                    *reinterpret_cast<float4*>(dst + i) = make_float4(a[0], a[1], a[2], a[3]);
+                }
+                mbar_arrive(&bars->v_full[s]);
+            }
+        } else {
+            mbar_arrive_expect_tx(&bars->v_full[s], C::V_TILE);
+        }
         for (int x = 0; x < C::V_BOXES; ++x)
             tma_load_4d(smem + C::SMEM_V + s * C::V_TILE + x * C::V_BOX_BYTES, &tmV, &bars->v_full[s],
                         x * (C::V_ROW / C::VB), n * BN, hkv, b, kEvictLast);
@@ -381,7 +420,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (lane < 4) {
             mbar_init(&bars->k_full[lane], 1);
             mbar_init(&bars->k_empty[lane], NQ);  // released by every tile's MMA warp
-            mbar_init(&bars->v_full[lane], 1);
+            mbar_init(&bars->v_full[lane], (TOKEN && !p.sk_bulk) ? 2 : 1);
             mbar_init(&bars->v_empty[lane], NQ);
         } else if (lane < 4 + NQ) {
             mbar_init(&bars->q_full[lane - 4], C::QTMEM ? 128 : 1);  // QTMEM: the tile's 128 rows, each put there by its thread
@@ -471,7 +510,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             auto issue_qk = [&](int stage, int half) {
                 const uint64_t bd = k_desc0 + uint64_t((stage * C::K_TILE + half * (BS * C::QK_ROW)) >> 4);
 #pragma unroll
-                for (int k = 0; k < D * C::QB / 32; ++k) {  // one MMA per 32-byte K slice (32 e4m3 / 16 bf16 elements)
+                for (int k = 0; k < (QA_ABL_QK > 0 ? QA_ABL_QK : D * C::QB / 32); ++k) {  // one MMA per 32-byte K slice (32 e4m3 / 16 bf16 elements)
                     if constexpr (C::QK16)
                         umma_f16_ss(s_t, q_desc + (qk_koff<C>(k) >> 4), bd + (qk_koff<C>(k) >> 4), idesc_qk, k > 0);
                     else if constexpr (C::QTMEM)
@@ -485,7 +524,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 const uint32_t p_t = p_t0 + (C::PBUFS == 2 ? half * 32 : 0);
                 const uint64_t bd = v_desc0 + uint64_t((stage * C::V_TILE + half * (BS * C::V_ROW)) >> 4);
 #pragma unroll
-                for (int k = 0; k < BS / KEYS_PER_PV; ++k) {
+                for (int k = 0; k < (QA_ABL_PV > 0 ? QA_ABL_PV : BS / KEYS_PER_PV); ++k) {
                     const uint64_t bk = bd + uint64_t((k * KEYS_PER_PV * C::V_ROW) >> 4);
                     if constexpr (!C::V16) {
                         umma_f8_ts(o_t, p_t + k * 8, bk, idesc_pv, (acc || k > 0) ? 1u : 0u);
@@ -608,26 +647,31 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         } else {
             c = p.scale_q[bh] * p.scale_k[bhkv] * p.sm_scale_log2;
         }
-        const float* sk_row = TOKEN ? p.scale_k + size_t(bhkv) * p.Skv : nullptr;
         const float2 c2 = make_float2(c, c);
 
         float m_used = -INFINITY;  // running max in raw score units (times per-column scale in token mode)
         float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);  // running sum of p' (4 partial sums)
         const int my_steps = n_steps(t);
 
-        // per-column K scales (token mode), applied to the raw scores of step j
+        // per-column K scales (token mode), applied to the raw scores of step j (called once per step, in order).  They
+        // come from shared memory, where the producer put the tile's 128 scales with its V boxes: the slot is refilled
+        // only after P V of the tile's second step, i.e. after every softmax thread has published that step's P.
+        int sk_slot = 0;
+        uint32_t sk_phase = 0;
+        const uint32_t sk_base = smem_u32(smem + C::SMEM_SK) + uint32_t(hf * CW * 4);
         auto kscale = [&](const int j, float (&s)[C::CW]) {
             if constexpr (TOKEN) {
-                const int col0 = j * BS + hf * CW;
-                if (col0 + CW <= p.Skv && (p.Skv & 3) == 0) {  // rows of scale_k stay 16-byte aligned
+                if ((j & 1) == 0) {
+                    if (j > 0 && ++sk_slot == C::STAGES) sk_slot = 0, sk_phase ^= 1;
+                    mbar_wait(&bars->v_full[sk_slot], sk_phase);  // (long complete: V_n is loaded ahead of P V_2n)
+                }
+                const uint32_t sk_addr = sk_base + uint32_t(sk_slot * (BN * 4) + (j & 1) * (BS * 4));
 #pragma unroll
-                    for (int i = 0; i < CW; i += 4) {
-                        float4 k4 = __ldg(reinterpret_cast<const float4*>(sk_row + col0 + i));
-                        s[i] *= k4.x, s[i + 1] *= k4.y, s[i + 2] *= k4.z, s[i + 3] *= k4.w;
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < CW; ++i) s[i] *= __ldg(sk_row + min(col0 + i, p.Skv - 1));
+                for (int i = 0; i < CW; i += 4) {
+                    const float4 k4 = lds_f32x4(sk_addr + i * 4);
+                    const float2 a = __fmul2_rn(make_float2(s[i], s[i + 1]), make_float2(k4.x, k4.y));
+                    const float2 bq = __fmul2_rn(make_float2(s[i + 2], s[i + 3]), make_float2(k4.z, k4.w));
+                    s[i] = a.x, s[i + 1] = a.y, s[i + 2] = bq.x, s[i + 3] = bq.y;
                 }
             }
         };
@@ -725,6 +769,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
             // p' for one pair of columns; a compile-time subset of the pairs avoids MUFU
             auto exp_pair = [&](int i) -> float2 {
+                if (QA_ABL_EXP > 0 && i >= QA_ABL_EXP) return make_float2(s[2 * i], s[2 * i + 1]);
                 const float2 x = __ffma2_rn(make_float2(s[2 * i], s[2 * i + 1]), c2, neg2);
                 if (pair_uses_poly(i, C::POLY_NUM)) return exp2_poly<C::POLY_DEG>(x);
                 return make_float2(ex2_approx(x.x), ex2_approx(x.y));
@@ -917,6 +962,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             int j = 0;
             bool need = true;  // first step: m_used = -inf
             for (; j + 2 <= n_fast; j += 2) {
+                __builtin_assume((j & 1) == 0);  // (token-wise: the K-scale slot advances on even steps)
                 mx = step(j, s_a, s_b, mx, need, false_type{}, false);
                 mx = step(j + 1, s_b, s_a, mx, need, false_type{}, false);
             }
@@ -1057,6 +1103,7 @@ static int launch_cfg(const AttnArgs& a, cudaStream_t stream, int* launches) {
     p.sm_scale_log2 = a.sm_scale * kLog2e;
     p.out_fp16 = (a.out_dtype == QA_DT_FP16);
     p.qk_fp16 = (a.qk_dtype == QA_DT_FP16);
+    p.sk_bulk = TOKEN && (a.Skv % 4 == 0) && (reinterpret_cast<uintptr_t>(a.scale_k) % 16 == 0);
     p.inv_group = float(a.Hkv) / float(a.Hq);
 #ifdef QA_TRACE
     p.trace = g_trace_ptr;

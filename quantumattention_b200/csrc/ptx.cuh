@@ -120,6 +120,12 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
           "r"(c2), "r"(c3), "l"(policy)
         : "memory");
 }
+// 16 bytes from shared memory by 32-bit shared address (volatile: stays behind the barrier wait that made the data visible)
+__device__ __forceinline__ float4 lds_f32x4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
 // 1-D bulk copy global -> shared (size and both addresses multiples of 16 bytes), completion on an mbarrier
 __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar,
                                              uint64_t policy) {

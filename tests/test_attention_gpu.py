@@ -147,6 +147,26 @@ def test_token_wise_scales(pv, causal):
     check(out, ref, pv, unit_scale=False, row_bound=0.03 if pv == "16bit" else None)
 
 
+@pytest.mark.parametrize("S,D,causal,hq,hkv,pv", [
+    (333, 64, False, 2, 2, "16bit"),     # Skv % 4 != 0: rows of scale_k are not 16-byte aligned (no bulk copy of the scales)
+    (1030, 128, True, 2, 2, "16bit"),    # ragged, not a multiple of 4 either, several trips round the K / V ring
+    (2052, 128, False, 4, 2, "16bit"),   # aligned rows + ragged tail (2052 = 16 * 128 + 4), GQA: scales of the kv head
+    (1500, 256, True, 2, 2, "16bit"),
+    (1500, 256, False, 2, 2, "fp8"),
+    (2052, 64, True, 2, 1, "fp8"),
+])
+def test_token_wise_shapes(S, D, causal, hq, hkv, pv):
+    """Per-token K scales travel to the softmax threads through shared memory (one bulk copy per K / V tile, or - when a
+    row of scale_k is not 16-byte aligned - plain loads by the producer lane): every head dimension, ragged tails, ring
+    wrap-around, GQA.  Semantics: inductor/kernels/attention.py:391-396,570-573 of the reference."""
+    g = torch.Generator().manual_seed(S + D)
+    q = torch.randn(1, hq, S, D, generator=g).to(torch.bfloat16)
+    k = (torch.randn(1, hkv, S, D, generator=g) * torch.exp(torch.randn(1, hkv, S, 1, generator=g))).to(torch.bfloat16)
+    v = torch.randn(1, hkv, S, D, generator=g).to(torch.bfloat16)
+    out, ref, _ = run_native(q, k, v, causal=causal, pv=pv, mode="token-wise")
+    check(out, ref, pv, tag=f"S{S} D{D}", unit_scale=False)
+
+
 @pytest.mark.parametrize("kind", ["outlier_channels", "huge_token", "zero_head"])
 def test_stress_inputs(kind):
     q, k, v = oracle.make_qkv(1, 2, 520, 520, 128, seed=6, kind=kind)
