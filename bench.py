@@ -298,7 +298,8 @@ def seq_sharded_block(dev, rank, world, dist, steps, warmup):
         split["note"] = ("one call of a back-to-back series, CUDA events on the compute stream: amax = local amax pass; scales = "
                          "all_reduce(MAX) of the head scales; quant_kv / quant_q = quantise with the global scales (K/V first: "
                          "they travel); transfer_exposed = time the compute stream waited for blocks; attention = the "
-                         "per-head-group launches")
+                         "per-head-group launches - or, gated_single_launch, the ONE launch over all heads whose CTAs "
+                         "wait for their head group's blocks themselves (the first group's transfer is then inside it)")
 
     # the transfer alone, by the transport in use: every head group's blocks, nothing else running
     wire_bytes = (world - 1) * B * H * S_loc * D * (1 + v_item)  # received per rank per step
@@ -381,6 +382,7 @@ def seq_sharded_block(dev, rank, world, dist, steps, warmup):
         "scaling": "strong", "n_gpus": world, "ms_per_step": ms, "steps": n, "value": fl / (ms * 1e-3) / 1e12, "unit": UNIT,
         "per_gpu_tflops": fl / (ms * 1e-3) / 1e12 / world, "pv_mode": pv_mode, "strategy": strategy,
         "transport": transport, "transport_error": transport_error, "head_groups": len(chunks),
+        "gated_single_launch": bool(strategy == "gather" and transport == "peer" and parallel.seq_gated_launch(B, H, S_loc)),
         "gpu_launches_per_step": launches,
         "one_gpu_ms_same_run": one_gpu_ms,
         "strong_scaling_efficiency": (one_gpu_ms / (world * ms)) if one_gpu_ms else None,

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define QA_ABI_VERSION 5
+#define QA_ABI_VERSION 6
 
 /* element types */
 #define QA_DT_BF16 0
@@ -126,6 +126,26 @@ int qa_fp8_attn_fwd(const void* q8, const void* k8, const void* v, int v_dtype, 
                     const int64_t* k_strides, const int64_t* v_strides, const float* scale_q, const float* scale_k,
                     const float* scale_v, int scale_mode, void* out, int out_dtype, float* lse, int B, int Hq, int Hkv,
                     int Sq, int Skv, int D, int causal, float sm_scale, int p_mode, void* stream);
+
+/* qa_fp8_attn_fwd as a GATED launch: the kernel starts at once, but the CTAs of kv head h read K / V only after the
+ * `flags_per_gate` 32-bit words kv_ready[(h / heads_per_gate) * flags_per_gate ...] are all non-zero.  The caller
+ * zero-fills the words on the launch stream before the call and sets each one with qa_set_flag on whatever stream
+ * brings that group of heads (one word per stream that carries a part of it).  New operator (the reference never
+ * shards a sequence): the sequence-sharded path attends ALL heads in ONE launch while the other ranks' K / V blocks
+ * of the later heads are still crossing NVLink on the copy engines - one launch keeps the hardware's dynamic CTA
+ * dispatch (fast SMs take more CTAs), where one launch per head group ran the groups in lock-step waves (each group
+ * waiting for the slowest CTA of the one before it: +12 % at 148 CTAs per group, profiles/r02_wave_probe.txt).
+ * Q must be complete in stream order (it is local).  Only for transfers that need no SM (copy engines): a transfer
+ * KERNEL could find every SM held by a polling CTA.  A flag that never arrives traps the kernel after ~4 s of polling.
+ */
+int qa_fp8_attn_fwd_gated(const void* q8, const void* k8, const void* v, int v_dtype, const int64_t* q_strides,
+                          const int64_t* k_strides, const int64_t* v_strides, const float* scale_q, const float* scale_k,
+                          const float* scale_v, int scale_mode, void* out, int out_dtype, float* lse, int B, int Hq,
+                          int Hkv, int Sq, int Skv, int D, int causal, float sm_scale, int p_mode,
+                          const unsigned* kv_ready, int heads_per_gate, int flags_per_gate, void* stream);
+/* *flag = non-zero in stream order, as a stream memory operation (cuStreamWriteValue32): no kernel, no SM - a kernel
+ * could never run while the gated launch it is to release holds every SM. */
+int qa_set_flag(unsigned* flag, void* stream);
 
 /* The whole of `fp8_attn_func` on 16-bit inputs in ONE call: quantise Q and K (and V in the FP8 P modes), then the
  * fused forward.  Replaces `_fp8_attention_wrapper` + the op call of the reference (src/quantum_attn/nn.py:394-430:

@@ -19,7 +19,7 @@ QA_SCALE_HEAD, QA_SCALE_TOKEN, QA_SCALE_HEAD_TWO_PASS, QA_SCALE_HEAD_AMAX_ONLY, 
 QA_SCALE_HEAD_RELOAD = 5
 QA_WS_PERSISTENT = 0x100  # qa_quantize_fp8: the workspace was zeroed once and is reused (include/qattn.h)
 QA_P_E4M3, QA_P_E4M3_HILO, QA_P_16BIT = 0, 1, 2
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 EXPORTED_SYMBOLS = (
     "qa_abi_version",
@@ -28,6 +28,8 @@ EXPORTED_SYMBOLS = (
     "qa_quantize_workspace_floats",
     "qa_quantize_fp8",
     "qa_fp8_attn_fwd",
+    "qa_fp8_attn_fwd_gated",
+    "qa_set_flag",
     "qa_fp8_attn_func",
     "qa_attn_fwd",
     "qa_merge_partials",
@@ -90,6 +92,10 @@ def load(build_if_missing: bool = True):
             ctypes.c_float, ctypes.c_int, vp,
         ]
         lib.qa_fp8_attn_fwd.restype = ctypes.c_int
+        lib.qa_fp8_attn_fwd_gated.argtypes = lib.qa_fp8_attn_fwd.argtypes[:-1] + [vp, ctypes.c_int, ctypes.c_int, vp]
+        lib.qa_fp8_attn_fwd_gated.restype = ctypes.c_int
+        lib.qa_set_flag.argtypes = [vp, vp]
+        lib.qa_set_flag.restype = ctypes.c_int
         lib.qa_fp8_attn_func.argtypes = (
             [vp, vp, vp, ctypes.c_int, i64p, i64p, i64p, vp, vp, vp, vp, vp, vp, vp, ctypes.c_int, vp, vp]
             + [ctypes.c_int] * 7 + [ctypes.c_float, ctypes.c_int, ctypes.c_int, vp])
@@ -291,10 +297,13 @@ def _f32c(t: Optional[torch.Tensor]):
 
 def fp8_attn_fwd(q8: torch.Tensor, k8: torch.Tensor, v: torch.Tensor, scale_q: torch.Tensor, scale_k: torch.Tensor,
                  scale_v: Optional[torch.Tensor], *, scale_mode: int, is_causal: bool, sm_scale: float, p_mode: int,
-                 out_dtype: torch.dtype, return_lse: bool = False, out: Optional[torch.Tensor] = None):
+                 out_dtype: torch.dtype, return_lse: bool = False, out: Optional[torch.Tensor] = None, gate=None):
     """Launch the fused forward kernel.  q8/k8 e4m3 [B,H,S,D]; v e4m3 (+scale_v) or bf16/fp16.  Tensors whose last
     dim is contiguous and whose strides are 16-byte multiples ([B,S,H,D]-held views) are read in place.  ``out``:
-    optional dense [B,Hq,Sq,D] destination (e.g. a head range of a larger output)."""
+    optional dense [B,Hq,Sq,D] destination (e.g. a head range of a larger output).  ``gate``: optional
+    (flags int32 tensor, heads_per_gate, flags_per_gate) - a gated launch (``qa_fp8_attn_fwd_gated``): the CTAs of kv
+    head h read K / V only once flags[(h // heads_per_gate) * flags_per_gate : ... + flags_per_gate] are non-zero
+    (``set_flag`` on the streams that bring them)."""
     lib = load()
     B, Hq, Sq, D = q8.shape
     Hkv, Skv = k8.shape[1], k8.shape[2]
@@ -320,12 +329,20 @@ def fp8_attn_fwd(q8: torch.Tensor, k8: torch.Tensor, v: torch.Tensor, scale_q: t
             tstream = torch.cuda.current_stream(dev)
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record(tstream)
-        rc = lib.qa_fp8_attn_fwd(
-            q8.data_ptr(), k8.data_ptr(), v.data_ptr(), _dt_code(v.dtype), qs, ks, vs, scale_q.data_ptr(),
-            scale_k.data_ptr(), scale_v.data_ptr() if scale_v is not None else None, scale_mode, out.data_ptr(),
-            _dt_code(out_dtype), lse.data_ptr() if lse is not None else None, B, Hq, Hkv, Sq, Skv, D,
-            int(bool(is_causal)), float(sm_scale), p_mode, stream,
-        )
+        common = (q8.data_ptr(), k8.data_ptr(), v.data_ptr(), _dt_code(v.dtype), qs, ks, vs, scale_q.data_ptr(),
+                  scale_k.data_ptr(), scale_v.data_ptr() if scale_v is not None else None, scale_mode, out.data_ptr(),
+                  _dt_code(out_dtype), lse.data_ptr() if lse is not None else None, B, Hq, Hkv, Sq, Skv, D,
+                  int(bool(is_causal)), float(sm_scale), p_mode)
+        if gate is None:
+            rc = lib.qa_fp8_attn_fwd(*common, stream)
+        else:
+            flags, heads_per_gate, flags_per_gate = gate
+            n_gates = -(-Hkv // int(heads_per_gate))
+            if flags.dtype != torch.int32 or flags.device != dev or not flags.is_contiguous() or \
+                    flags.numel() < n_gates * int(flags_per_gate):
+                raise ValueError("fp8_attn_fwd: `gate` needs a dense int32 flag tensor on the inputs' device with "
+                                 "ceil(Hkv / heads_per_gate) * flags_per_gate words")
+            rc = lib.qa_fp8_attn_fwd_gated(*common, flags.data_ptr(), int(heads_per_gate), int(flags_per_gate), stream)
         if attn_events is not None:
             ev1.record(tstream)
             attn_events.append((ev0, ev1))
@@ -456,6 +473,11 @@ def merge_partials(o_acc: Optional[torch.Tensor], lse_acc: torch.Tensor, o_new: 
 def copy_2d(dst_ptr: int, dst_pitch: int, src_ptr: int, src_pitch: int, width_bytes: int, rows: int, stream: int) -> None:
     """Asynchronous strided block copy on the copy engines (``qa_copy_2d``); raw device addresses and a raw stream."""
     _check(load().qa_copy_2d(dst_ptr, dst_pitch, src_ptr, src_pitch, width_bytes, rows, stream), "qa_copy_2d")
+
+
+def set_flag(flags: torch.Tensor, index: int, raw_stream: int) -> None:
+    """flags[index] = non-zero in the order of ``raw_stream`` (a memset node behind the copies it vouches for)."""
+    _check(load().qa_set_flag(flags.data_ptr() + 4 * int(index), raw_stream), "qa_set_flag")
 
 
 class CopyBatch:

@@ -3,6 +3,8 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cuda.h>
+#include <mutex>
 #include "qattn_internal.h"
 
 namespace qa {
@@ -146,8 +148,11 @@ int qa_quantize_fp8(int n_tensors, const void* const* x, int x_dtype, const int6
 static int fp8_attn_call(const void* q8, const void* k8, const void* v, int v_dtype, const int64_t* q_strides,
                          const int64_t* k_strides, const int64_t* v_strides, const float* scale_q, const float* scale_k,
                          const float* scale_v, int scale_mode, void* out, int out_dtype, float* lse, int B, int Hq,
-                         int Hkv, int Sq, int Skv, int D, int causal, float sm_scale, int p_mode, void* stream) {
+                         int Hkv, int Sq, int Skv, int D, int causal, float sm_scale, int p_mode, void* stream,
+                         const unsigned* kv_ready = nullptr, int gate_heads = 1, int gate_flags = 0) {
     if (!q8 || !k8 || !v || !scale_q || !scale_k || !out) return set_error(QA_ERR_INVALID, "null pointer argument");
+    if (kv_ready && (gate_heads < 1 || gate_flags < 1 || gate_flags > 64))
+        return set_error(QA_ERR_INVALID, "gated launch: heads_per_gate >= 1 and 1 <= flags_per_gate <= 64 expected");
     if (D != 64 && D != 128 && D != 256) return set_error(QA_ERR_INVALID, "Unsupported head dimension: %d", D);
     if (B < 1 || Hq < 1 || Hkv < 1 || Sq < 1 || Skv < 1) return set_error(QA_ERR_INVALID, "empty problem");
     if (Hq % Hkv != 0)
@@ -188,7 +193,44 @@ static int fp8_attn_call(const void* q8, const void* k8, const void* v, int v_dt
     a.v_dtype = v_dtype;
     a.out_dtype = out_dtype;
     a.qk_dtype = QA_DT_E4M3;
+    a.kv_ready = kv_ready, a.gate_heads = gate_heads, a.gate_flags = kv_ready ? gate_flags : 0;
     return attn_fwd_dispatch(a, static_cast<cudaStream_t>(stream), &g_launches);
+}
+
+int qa_fp8_attn_fwd_gated(const void* q8, const void* k8, const void* v, int v_dtype, const int64_t* q_strides,
+                          const int64_t* k_strides, const int64_t* v_strides, const float* scale_q, const float* scale_k,
+                          const float* scale_v, int scale_mode, void* out, int out_dtype, float* lse, int B, int Hq,
+                          int Hkv, int Sq, int Skv, int D, int causal, float sm_scale, int p_mode,
+                          const unsigned* kv_ready, int heads_per_gate, int flags_per_gate, void* stream) {
+    g_launches = 0;
+    if (!kv_ready) return set_error(QA_ERR_INVALID, "null pointer argument");
+    return fp8_attn_call(q8, k8, v, v_dtype, q_strides, k_strides, v_strides, scale_q, scale_k, scale_v, scale_mode, out,
+                         out_dtype, lse, B, Hq, Hkv, Sq, Skv, D, causal, sm_scale, p_mode, stream, kv_ready,
+                         heads_per_gate, flags_per_gate);
+}
+
+int qa_set_flag(unsigned* flag, void* stream) {
+    g_launches = 0;
+    if (!flag) return set_error(QA_ERR_INVALID, "null pointer argument");
+    // A stream memory operation (cuStreamWriteValue32): performed by the stream's front end in stream order behind the
+    // copies it vouches for.  NOT cudaMemsetAsync: a small memset is a kernel, and the gated attention kernel it would
+    // release holds every SM (one CTA per SM, the whole register file) while it polls - the memset would never run.
+    typedef CUresult (*PFN_write32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+    static PFN_write32 fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_write32>(p);
+    });
+    if (!fn) return set_error(QA_ERR_DEVICE, "cuStreamWriteValue32 is unavailable (no CUDA driver?)");
+    int rc = check_device();
+    if (rc != QA_OK) return rc;
+    CUresult r = fn(static_cast<CUstream>(stream), reinterpret_cast<CUdeviceptr>(flag), 0x01010101u, 0u);
+    if (r != CUDA_SUCCESS) return set_error(QA_ERR_CUDA, "cuStreamWriteValue32 failed with CUresult %d", int(r));
+    return QA_OK;
 }
 
 int qa_fp8_attn_fwd(const void* q8, const void* k8, const void* v, int v_dtype, const int64_t* q_strides,

@@ -256,6 +256,10 @@ struct AttnParams {
     int out_fp16;
     int qk_fp16;  // QK16 configs: element type of Q and K
     int sk_bulk;  // token-wise: rows of scale_k are 16-byte aligned -> staged through shared memory by bulk copies
+    // gated launch (qa_fp8_attn_fwd_gated): K / V of kv head h are only read once the `gate_flags` words from
+    // kv_ready[(h / gate_heads) * gate_flags] on are all non-zero (set in stream order behind the copies that bring them)
+    const unsigned* kv_ready;
+    int gate_heads, gate_flags;
     float inv_group;  // Hkv / Hq
     long long* trace;  // developer builds (-DQA_TRACE): per-step clock64 stamps of one CTA, else unused
     int trace_x, trace_y;
@@ -433,6 +437,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             tma_prefetch_desc(&tmV);
             tma_prefetch_desc(&tmO);
             griddep_wait();
+            if (p.kv_ready != nullptr) {
+                // gated launch: this head's K / V may still be on their way (copy engines, another stream).  A bounded
+                // poll: a transfer that never completes becomes a trap, not a hang.
+                const unsigned* f = p.kv_ready + (hkv / p.gate_heads) * p.gate_flags;
+                for (int i = 0; i < p.gate_flags; ++i) {
+                    unsigned spins = 0;
+                    while (ld_acquire_sys_u32(f + i) == 0u) {
+                        __nanosleep(128);
+                        if (++spins > (1u << 25)) __trap();
+                    }
+                }
+                fence_proxy_async_global();  // the TMA engine (async proxy) reads what the flags vouch for
+            }
             if constexpr (C::QTMEM) {
                 load_kv(0);
             } else {
@@ -1104,6 +1121,7 @@ static int launch_cfg(const AttnArgs& a, cudaStream_t stream, int* launches) {
     p.out_fp16 = (a.out_dtype == QA_DT_FP16);
     p.qk_fp16 = (a.qk_dtype == QA_DT_FP16);
     p.sk_bulk = TOKEN && (a.Skv % 4 == 0) && (reinterpret_cast<uintptr_t>(a.scale_k) % 16 == 0);
+    p.kv_ready = a.kv_ready, p.gate_heads = a.gate_heads > 0 ? a.gate_heads : 1, p.gate_flags = a.gate_flags;
     p.inv_group = float(a.Hkv) / float(a.Hq);
 #ifdef QA_TRACE
     p.trace = g_trace_ptr;

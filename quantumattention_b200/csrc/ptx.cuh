@@ -120,6 +120,13 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
           "r"(c2), "r"(c3), "l"(policy)
         : "memory");
 }
+__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// generic-proxy -> async-proxy ordering for global memory (a flag was read with ld.acquire, TMA loads follow)
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 // 16 bytes from shared memory by 32-bit shared address (volatile: stays behind the barrier wait that made the data visible)
 __device__ __forceinline__ float4 lds_f32x4(uint32_t addr) {
     float4 v;

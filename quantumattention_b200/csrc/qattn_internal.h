@@ -105,6 +105,8 @@ struct AttnArgs {
     int out_dtype;
     int qk_dtype;  // QA_DT_E4M3 (FP8 path) or QA_DT_BF16 / QA_DT_FP16 (16-bit path)
     int64_t qs[3], ks[3], vs[3];  // element strides (batch, head, row) of q8 / k8 / v; the last dim is contiguous
+    const unsigned* kv_ready = nullptr;  // gated launch: see AttnParams
+    int gate_heads = 1, gate_flags = 0;
 };
 
 struct MergeArgs {

@@ -85,9 +85,10 @@ class NativeBackend:
         outs, _ = _native.quantize_fp8(list(tensors), _native.QA_SCALE_HEAD_GIVEN, scales=list(scales), outs=outs)
         return outs
 
-    def attend(self, q8, k8, v, sq, sk, sv, sm_scale, p_mode, out_dtype, out=None, return_lse=True):
+    def attend(self, q8, k8, v, sq, sk, sv, sm_scale, p_mode, out_dtype, out=None, return_lse=True, gate=None):
         return _native.fp8_attn_fwd(q8, k8, v, sq, sk, sv, scale_mode=_native.QA_SCALE_HEAD, is_causal=False,
-                                    sm_scale=sm_scale, p_mode=p_mode, out_dtype=out_dtype, return_lse=return_lse, out=out)
+                                    sm_scale=sm_scale, p_mode=p_mode, out_dtype=out_dtype, return_lse=return_lse, out=out,
+                                    gate=gate)
 
     def merge(self, o_acc, lse_acc, o_new, lse_new, first, out=None):
         _native.merge_partials(o_acc, lse_acc, o_new, lse_new, first=first, out=out)
@@ -141,6 +142,19 @@ def default_seq_transport() -> str:
     if s not in SEQ_TRANSPORTS:
         raise ValueError(f"QA_SEQ_TRANSPORT must be one of {SEQ_TRANSPORTS} but got {s!r}")
     return s
+
+
+def seq_gated_launch(B: int = 1, H: int = 1 << 20, S_local: int = 1 << 20, n_sms: int = 148) -> bool:
+    """Should the gather strategy (peer transport) attend ALL heads in ONE gated launch (``qa_fp8_attn_fwd_gated``: the
+    CTAs of a head group poll a flag its copies set) instead of one launch per head group?  Per-group launches run in
+    lock-step - each waits for the slowest CTA of the one before - while one launch lets fast SMs take more CTAs; that
+    only pays when an SM gets enough CTAs per call to balance with.  Measured on C4 (strong-scaling efficiency, gated
+    against per-group): N = 4 (12 CTAs per SM) 0.974 / 0.950; N = 8 (6 per SM) 0.923 / 0.954.  ``QA_SEQ_GATED`` = 1 / 0
+    forces it on / off; default: on from 8 CTAs per SM."""
+    env = os.environ.get("QA_SEQ_GATED", "auto")
+    if env in ("0", "1"):
+        return env == "1"
+    return B * H * ((S_local + 255) // 256) >= 8 * n_sms
 
 
 _peer_unavailable = {}  # id(group) -> reason the peer transport could not be set up (then "auto" means NCCL)
@@ -255,6 +269,8 @@ class PeerGather:
         self.cur = 0
         self.phase = 0
         B, H, S, D = k_shape
+        # gated launch: one word per (head group, copy stream), set behind the group's copies on that stream
+        self.flags = torch.zeros((64 * len(self.streams),), dtype=torch.int32, device=device)
         self.k_all = torch.empty((B, H, self.world * S, D), dtype=torch.uint8, device=device)
         self.v_all = torch.empty((B, H, self.world * S, D * v_itemsize), dtype=torch.uint8, device=device)
 
@@ -275,12 +291,13 @@ class PeerGather:
             st.wait_event(ready)
         self.cur, self.phase = self.phase, self.phase ^ 1
 
-    def pull_group(self, lo: int, hi: int) -> List[torch.cuda.Event]:
-        """Start the pulls of heads [lo, hi) from every rank (own block: a local copy); returns the events to wait for.
+    def pull_group(self, lo: int, hi: int, gate_index: Optional[int] = None) -> List[torch.cuda.Event]:
+        """Start the pulls of heads [lo, hi) from every rank (own block: a local copy); returns the events to wait for -
+        or, with ``gate_index``, sets the group's words of ``self.flags`` behind the copies instead (gated launch).
         The copies are dealt round-robin to a few streams so that transfers from different peers overlap; the argument
         arrays of a (slot, head range) are marshalled once and re-issued with one call of the C ABI - the host cost of
         issuing the copies is what the first head group's transfer hides behind, so it has to be small."""
-        key = (self.cur, lo, hi)
+        key = (self.cur, lo, hi, gate_index is not None)
         batch = self.batches.get(key)
         if batch is None:
             B, H, S_all, D = self.k_all.shape
@@ -290,7 +307,10 @@ class PeerGather:
             k_dst, v_dst = self.k_all.data_ptr(), self.v_all.data_ptr()
             raws = [st.cuda_stream for st in self.streams]
             copies, n = [], 0
-            for i in range(self.world):
+            # (gated launch: the own block is NOT pulled here - a device-local 2-D copy is a kernel, and no kernel can run
+            # while the polling attention launch holds every SM; fill_own() puts it in place before the launch.  Copies
+            # from PEER memory run on the copy engines: scripts/gate_probe.py)
+            for i in range(1 if gate_index is not None else 0, self.world):
                 r = (self.rank + i) % self.world  # own block first, then the peers - every rank in another order
                 src = self.peer_ptrs[r] + base
                 for b in range(B):
@@ -302,12 +322,25 @@ class PeerGather:
                     n += 2
             batch = self.batches[key] = _native.CopyBatch(copies)
         batch.issue()
+        if gate_index is not None:
+            for i, st in enumerate(self.streams):
+                _native.set_flag(self.flags, gate_index * len(self.streams) + i, st.cuda_stream)
+            return []
         evs = []
         for st in self.streams:
             ev = torch.cuda.Event()
             ev.record(st)
             evs.append(ev)
         return evs
+
+    def fill_own(self, kb: torch.Tensor, vb: torch.Tensor) -> None:
+        """This rank's own blocks (all heads) into their place in the per-head layout, on the calling stream."""
+        B, H, S_all, D = self.k_all.shape
+        S, Dv = S_all // self.world, self.v_all.shape[-1]
+        raw = torch.cuda.current_stream(self.device).cuda_stream
+        # one strided copy per tensor: row (b, h) = this rank's S x D bytes, S_all x D apart in the per-head layout
+        _native.copy_2d(self.k_all.data_ptr() + self.rank * S * D, S_all * D, kb.data_ptr(), S * D, S * D, B * H, raw)
+        _native.copy_2d(self.v_all.data_ptr() + self.rank * S * Dv, S_all * Dv, vb.data_ptr(), S * Dv, S * Dv, B * H, raw)
 
     def pull(self, chunks: Sequence[Tuple[int, int]]) -> List[List[torch.cuda.Event]]:
         """start() + every head group at once (bench.py's transfer-alone probe)."""
@@ -387,9 +420,31 @@ def ring_fp8_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, sca
                 vb.view(v.dtype).copy_(v)
             else:
                 be.quantize([k, v], [sk, sv], outs=[kb, vb])
+            gated = seq_gated_launch(B, H, S) and len(chunks) <= 64
+            if gated:
+                comm.flags.zero_()  # (on the calling stream, ahead of the event the copy streams wait for)
             comm.start()
             k_all = comm.k_all.view(f8)
             v_all = comm.v_all.view(v.dtype if v16 else f8)
+            if gated:
+                # ONE launch over all heads; the copies of head group g set the group's flags behind them and the CTAs of
+                # its heads wait for those.  The first group's copies go out before Q is quantised, the launch follows,
+                # and the host issues the later groups' copies while the kernel already runs.
+                hc = chunks[0][1] - chunks[0][0]
+                comm.pull_group(*chunks[0], gate_index=0)
+                comm.fill_own(kb, vb)  # (kernels on this stream, under the first group's transfer)
+                _mark("quant_kv", q.device)
+                (q8,) = be.quantize([q], [sq])
+                _mark("quant_q", q.device)
+                dst = out if out.is_contiguous() else None
+                o = be.attend(q8, k_all, v_all, sq, sk, None if v16 else sv, sm_scale, p_mode, q.dtype, out=dst,
+                              return_lse=False, gate=(comm.flags, hc, len(comm.streams)))
+                for i in range(1, len(chunks)):
+                    comm.pull_group(*chunks[i], gate_index=i)
+                if dst is None:
+                    out.copy_(o)
+                _mark("attend", q.device)
+                return out
             fetch = lambda lo, hi: comm.pull_group(lo, hi)
 
             def wait(evs):

@@ -46,6 +46,14 @@ def test_argument_validation_without_gpu():
     assert rc == -1 and b"multiple of Hkv" in lib.qa_last_error()
     rc = lib.qa_fp8_attn_fwd(16, 16, 16, 0, None, None, None, 16, 16, None, 0, 16, 0, None, 1, 2, 2, 8, 8, 64, 0, 0.125, 0, None)
     assert rc == -1  # fp8 P mode with a 16-bit V
+    # gated launch: flags are required, and a sane gate geometry
+    rc = lib.qa_fp8_attn_fwd_gated(16, 16, 16, 2, None, None, None, 16, 16, 16, 0, 32, 0, None, 1, 2, 2, 8, 8, 64, 0, 0.125, 2,
+                                   None, 1, 1, None)
+    assert rc == -1
+    rc = lib.qa_fp8_attn_fwd_gated(16, 16, 16, 2, None, None, None, 16, 16, 16, 0, 32, 0, None, 1, 2, 2, 8, 8, 64, 0, 0.125, 2,
+                                   16, 0, 1, None)
+    assert rc == -1 and b"gated launch" in lib.qa_last_error()
+    assert lib.qa_set_flag(None, None) == -1
     rc = lib.qa_attn_fwd(16, 16, 16, 2, None, None, None, 16, None, 1, 2, 2, 8, 8, 64, 0, 0.125, None)
     assert rc == -1 and b"fp16 or bf16" in lib.qa_last_error()  # e4m3 inputs belong to qa_fp8_attn_fwd
     rc = lib.qa_attn_fwd(16, 16, 16, 0, None, None, None, 16, None, 1, 2, 2, 8, 8, 96, 0, 0.125, None)

@@ -133,6 +133,17 @@ def test_merge_ref_is_exact_split_softmax():
     assert torch.equal(o2, oa) and torch.equal(l2, la)
 
 
+def test_gated_launch_is_chosen_when_an_sm_gets_enough_ctas(monkeypatch):
+    """One gated launch over all heads pays from 8 CTAs per SM per call (C4: N = 2 and 4, not N = 8); QA_SEQ_GATED forces."""
+    monkeypatch.delenv("QA_SEQ_GATED", raising=False)
+    assert parallel.seq_gated_launch(1, 24, 37800) and parallel.seq_gated_launch(1, 24, 18900)
+    assert not parallel.seq_gated_launch(1, 24, 9450)
+    monkeypatch.setenv("QA_SEQ_GATED", "1")
+    assert parallel.seq_gated_launch(1, 24, 9450)
+    monkeypatch.setenv("QA_SEQ_GATED", "0")
+    assert not parallel.seq_gated_launch(1, 24, 37800)
+
+
 def test_head_chunks_fill_whole_waves():
     """Head groups of the gather strategy: contiguous, cover every head once, and sized so a launch fills the SMs in
     whole waves where the shape allows it (C4 over 8 / 4 / 2 ranks: 37 / 74 / 148 CTAs per head on 148 SMs)."""

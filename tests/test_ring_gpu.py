@@ -144,6 +144,40 @@ def test_head_group_launches_over_gathered_layout_equal_one_launch():
     assert not q8[:, 1:3].is_contiguous() and torch.equal(part, whole[:, 1:3])
 
 
+def test_gated_launch_reads_a_head_group_only_behind_its_flags():
+    """qa_fp8_attn_fwd_gated: the kernel is launched while K / V of the head groups are still being written on ANOTHER
+    stream; each group's flags are set behind its copies.  The result must be that of the plain launch on the final
+    bytes (an early read would see the zero-filled buffers), and the launch must have lasted as long as the delay."""
+    B, H, S, D = 1, 4, 640, 128
+    q, k, v = (t.cuda() for t in oracle.make_qkv(B, H, S, S, D, seed=12))
+    (q8, k8), (sq, sk) = _native.quantize_fp8([q, k], _native.QA_SCALE_HEAD)
+    kw = dict(scale_mode=_native.QA_SCALE_HEAD, is_causal=False, sm_scale=1 / math.sqrt(D), p_mode=_native.QA_P_16BIT,
+              out_dtype=torch.bfloat16)
+    ref = _native.fp8_attn_fwd(q8, k8, v, sq, sk, None, **kw)
+    main, side = torch.cuda.current_stream(), torch.cuda.Stream()
+    for rep in range(2):  # (second round: flags re-zeroed on the launch stream, as the sequence-sharded path does)
+        k_buf, v_buf = torch.zeros_like(k8.view(torch.uint8)).view(k8.dtype), torch.zeros_like(v)
+        flags = torch.zeros(4, dtype=torch.int32, device="cuda")  # 2 gates (2 heads each) x 2 flags
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(side):
+            for g in (1, 0):  # the LATER head group first: order of arrival is free
+                torch.cuda._sleep(20_000_000)  # ~10 ms
+                k_buf[:, 2 * g:2 * g + 2].copy_(k8[:, 2 * g:2 * g + 2])
+                v_buf[:, 2 * g:2 * g + 2].copy_(v[:, 2 * g:2 * g + 2])
+                _native.set_flag(flags, 2 * g, side.cuda_stream)
+                _native.set_flag(flags, 2 * g + 1, side.cuda_stream)
+        e0.record(main)
+        out = _native.fp8_attn_fwd(q8, k_buf, v_buf, sq, sk, None, gate=(flags, 2, 2), **kw)
+        e1.record(main)
+        torch.cuda.synchronize()
+        assert torch.equal(out, ref)
+        assert e0.elapsed_time(e1) > 10.0, e0.elapsed_time(e1)  # it waited for the second group's flags
+        assert flags.tolist() == [0x01010101] * 4
+    with pytest.raises(ValueError):
+        _native.fp8_attn_fwd(q8, k8, v, sq, sk, None, gate=(flags[:1], 2, 2), **kw)
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -168,9 +202,11 @@ def _nccl_worker(rank, world, port, tmp):
         for pv in ("16bit", "fp8", "fp8_hilo"):
             with quantum_attn.config.patch({"attention.pv_mode": pv}):
                 whole = quantum_attn.fp8_attn_func(q.cuda(), k.cuda(), v.cuda())[:, :, sl]
-            for strategy, transport in (("gather", "nccl"), ("gather", "peer"), ("ring", "nccl")):
+            for strategy, transport, gated in (("gather", "nccl", "1"), ("gather", "peer", "1"), ("gather", "peer", "0"),
+                                               ("ring", "nccl", "1")):
                 if transport == "peer" and peer_error is not None:
                     continue
+                os.environ["QA_SEQ_GATED"] = gated  # peer transport: one gated launch over all heads / one per group
                 try:
                     for rep in range(3):  # repeated calls: the peer transport alternates its two send slots
                         out = parallel.ring_fp8_attention(*loc, pv_mode=pv, strategy=strategy, transport=transport,
@@ -181,7 +217,7 @@ def _nccl_worker(rank, world, port, tmp):
                         raise
                     peer_error = repr(e)[:300]
                     continue
-                res[(pv, strategy, transport)] = (out.cpu(), whole.cpu())
+                res[(pv, strategy, transport + ("" if gated == "1" else "-ungated"))] = (out.cpu(), whole.cpu())
         torch.save({"res": res, "peer_error": peer_error}, os.path.join(tmp, f"r{rank}.pt"))
     finally:
         dist.destroy_process_group()
