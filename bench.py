@@ -67,6 +67,7 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
         self._stop_evt = threading.Event()
+        self.recording = threading.Event()  # samples are kept only while this is set (the timed region)
         self.ok = False
         try:
             import pynvml
@@ -91,14 +92,16 @@ class ClockSampler(threading.Thread):
         }
         while not self._stop_evt.is_set():
             try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
                 try:
                     r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
                 except Exception:
                     r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for bit, name in names.items():
-                    if r & bit:
-                        self.reasons.add(name)
+                if self.recording.is_set():
+                    self.samples.append(mhz)
+                    for bit, name in names.items():
+                        if r & bit:
+                            self.reasons.add(name)
             except Exception:
                 pass
             time.sleep(0.002)
@@ -649,12 +652,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # the NVML sampler thread is started BEFORE the warm-up (NVML initialisation and its first queries take driver
+    # locks the launch path also wants: inside a 4 ms timed region that showed up as 10-20 us per step); it keeps
+    # samples only while `recording` is set
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for i in range(max(args.warmup, 3)):
         step(i)
     barrier()
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.recording.set()
     _native.attn_events = []
     launches0 = _native.launch_total
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -13,7 +13,7 @@ timeout 900 python bench.py --workload C4_video --no-cpu-baseline > gpurun_out/b
 timeout 600 python bench.py --workload C1 --no-cpu-baseline --no-comparators > gpurun_out/bench_c1_$R.json 2> gpurun_out/bench_c1_$R.err
 timeout 600 python bench.py --pv-mode fp8 --no-cpu-baseline --no-comparators > gpurun_out/bench_c2_fp8_$R.json 2> gpurun_out/bench_c2_fp8_$R.err
 timeout 300 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref_$R.json 2> gpurun_out/bench_ref_$R.err
-timeout 600 python scripts/ab_kernels.py $R > gpurun_out/kernels_$R.txt 2>&1
+AB_MODES=16bit,fp8,hilo,token timeout 600 python scripts/ab_kernels.py $R > gpurun_out/kernels_$R.txt 2>&1
 timeout 300 python scripts/quant_time.py > gpurun_out/quant_time_$R.txt 2>&1
 timeout 400 python scripts/cutedsl_fmha_bar.py > gpurun_out/cutedsl_$R.log 2>&1
 for tool in memcheck racecheck; do timeout 900 compute-sanitizer --tool $tool --print-limit 20 python scripts/sanitize_small.py > gpurun_out/sanitizer_${tool}_$R.txt 2>&1; done
