@@ -121,6 +121,9 @@ constexpr float kLog2e = 1.4426950408889634f;
 #ifndef QA_ABL_EXP
 #define QA_ABL_EXP 0   // > 0: only the first this-many pairs (of 32) of a step's scores go through scale + exp2
 #endif
+#ifndef QA_WARP_ARRIVE
+#define QA_WARP_ARRIVE 0  // 1: one elected lane per softmax warp arrives on s_free / p_full / q_full (4 arrivals instead of 128)
+#endif
 #ifndef QA_SPLIT
 #define QA_SPLIT 0     // 1: TWO softmax threads per query row (each owns half of a step's 64 columns): 4 softmax warps per scheduler
 #endif
@@ -275,6 +278,18 @@ struct Barriers {
 };
 static_assert(sizeof(Barriers) <= 512, "barrier block too large");
 
+// Arrival of a softmax warp on a barrier its query tile's MMA warp waits for.  The tcgen05.ld / .st the arrival vouches for
+// are warp-collective and each lane has fenced them, so after a warp sync one lane can arrive for all 32.
+constexpr int kTileArrivals = QA_WARP_ARRIVE ? 4 : 128;  // per tile and softmax thread share
+__device__ __forceinline__ void softmax_arrive(uint64_t* bar) {
+#if QA_WARP_ARRIVE
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+#else
+    mbar_arrive(bar);
+#endif
+}
+
 template <class C>
 __device__ __forceinline__ uint32_t qk_koff(int k) {  // byte offset of the k-th 32-byte K slice inside a Q/K tile
     constexpr int per_box = C::QK_ROW / 32;
@@ -375,8 +390,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             const int t = lane >> 1, x = lane & 1;
             if (x) mbar_init(&bars->o_full[t], 1);
             mbar_init(&bars->pv_done[t][x], 1);
-            mbar_init(&bars->p_full[t][x], 128 * C::NH);
-            mbar_init(x ? &bars->s_free[t] : &bars->s_full[t], x ? 128 * C::NH : 1);
+            mbar_init(&bars->p_full[t][x], kTileArrivals * C::NH);
+            mbar_init(x ? &bars->s_free[t] : &bars->s_full[t], x ? kTileArrivals * C::NH : 1);
         }
         fence_barrier_init();
     }
@@ -427,7 +442,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             mbar_init(&bars->v_full[lane], (TOKEN && !p.sk_bulk) ? 2 : 1);
             mbar_init(&bars->v_empty[lane], NQ);
         } else if (lane < 4 + NQ) {
-            mbar_init(&bars->q_full[lane - 4], C::QTMEM ? 128 : 1);  // QTMEM: the tile's 128 rows, each put there by its thread
+            mbar_init(&bars->q_full[lane - 4], C::QTMEM ? kTileArrivals : 1);  // QTMEM: the tile's 128 rows, each put there by its thread
         }
         fence_barrier_init();
         __syncwarp();
@@ -771,7 +786,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     // even start before P_{j-1} is published
                     tmem_st_wait();
                     tc_fence_before();
-                    mbar_arrive(&bars->p_full[t][(j - 1) & 1]);
+                    softmax_arrive(&bars->p_full[t][(j - 1) & 1]);
                     p_prev_pending = false;
                     // (one barrier per step parity: PV_{j-3}, the previous phase of this barrier, is known to be
                     // complete because S_j has been seen, so the parity test cannot alias)
@@ -831,7 +846,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             if (p_prev_pending) {  // P_{j-1} was stored at the end of the previous step: publish it now
                 tmem_st_wait();
                 tc_fence_before();
-                mbar_arrive(&bars->p_full[t][(j - 1) & 1]);
+                softmax_arrive(&bars->p_full[t][(j - 1) & 1]);
             }
 #pragma unroll
             for (int i = PUBQ; i < LOADQ - PROBEQ; ++i) exp_quad(i);
@@ -854,7 +869,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 for (int i = LOADQ; i < LOADQ + LDW; ++i) exp_quad(i);
                 tmem_ld_wait();
                 tc_fence_before();
-                mbar_arrive(&bars->s_free[t]);  // the score buffer may be overwritten by QK_{j+2}
+                softmax_arrive(&bars->s_free[t]);  // the score buffer may be overwritten by QK_{j+2}
                 kscale(j + 1, s_next);
                 if constexpr (MASKED) mask(j + 1, s_next);
                 QA_STAMP(t, j, 3);
@@ -916,7 +931,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             if (last) {  // nothing left to hide the store behind
                 tmem_st_wait();
                 tc_fence_before();
-                mbar_arrive(&bars->p_full[t][j & 1]);
+                softmax_arrive(&bars->p_full[t][j & 1]);
             }
             QA_STAMP(t, j, 4);
             return fmaxf(ma, mb);
@@ -949,7 +964,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 }
                 tmem_st_wait();
                 tc_fence_before();
-                mbar_arrive(&bars->q_full[t]);
+                softmax_arrive(&bars->q_full[t]);
             }
         }
         float s_a[CW], s_b[CW];
@@ -963,7 +978,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             else tmem_ld_x32(s_addr, s_a);
             tmem_ld_wait();
             tc_fence_before();
-            mbar_arrive(&bars->s_free[t]);
+            softmax_arrive(&bars->s_free[t]);
             kscale(0, s_a);
             mask(0, s_a);
             float ma = -INFINITY, mb = -INFINITY;
