@@ -476,7 +476,8 @@ def copy_2d(dst_ptr: int, dst_pitch: int, src_ptr: int, src_pitch: int, width_by
 
 
 def set_flag(flags: torch.Tensor, index: int, raw_stream: int) -> None:
-    """flags[index] = non-zero in the order of ``raw_stream`` (a memset node behind the copies it vouches for)."""
+    """flags[index] = non-zero in the order of ``raw_stream`` (``qa_set_flag``: a stream memory operation behind the
+    copies it vouches for - no kernel, so it completes even while a polling launch holds every SM)."""
     _check(load().qa_set_flag(flags.data_ptr() + 4 * int(index), raw_stream), "qa_set_flag")
 
 

@@ -414,19 +414,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 bulk_load_1d(smem + C::SMEM_SK + s * (BN * 4), p.scale_k + size_t(bhkv) * p.Skv + size_t(n) * BN, sk_bytes,
                              &bars->v_full[s], kEvictLast);
             } else {
-                // rows of scale_k not 16-byte aligned (Skv % 4 != 0): no bulk copy - this lane moves the 128 scales itself
-                // and arrives a second time (the barrier then counts two arrivals per phase)
+                // rows of scale_k not 16-byte aligned (Skv % 4 != 0): no bulk copy - the whole producer warp moves the 128
+                // scales with plain loads (load_sk_warp) and arrives a second time: the barrier counts two arrivals per phase
                 mbar_arrive_expect_tx(&bars->v_full[s], C::V_TILE);
-                const float* src = p.scale_k + size_t(bhkv) * p.Skv;
-                float* dst = reinterpret_cast<float*>(smem + C::SMEM_SK + s * (BN * 4));
-#pragma unroll 4
-                for (int i = 0; i < BN; i += 4) {
-                    float a[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) a[u] = __ldg(src + min(n * BN + i + u, p.Skv - 1));
-                    *reinterpret_cast<float4*>(dst + i) = make_float4(a[0], a[1], a[2], a[3]);
-                }
-                mbar_arrive(&bars->v_full[s]);
             }
         } else {
             mbar_arrive_expect_tx(&bars->v_full[s], C::V_TILE);
@@ -434,6 +424,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         for (int x = 0; x < C::V_BOXES; ++x)
             tma_load_4d(smem + C::SMEM_V + s * C::V_TILE + x * C::V_BOX_BYTES, &tmV, &bars->v_full[s],
                         x * (C::V_ROW / C::VB), n * BN, hkv, b, kEvictLast);
+    };
+    auto load_sk_warp = [&](int n) {  // (whole warp, converged; slot `s` is known to be free)
+        const int s = n % C::STAGES;
+        const float* src = p.scale_k + size_t(bhkv) * p.Skv;
+        float a[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) a[u] = __ldg(src + min(n * BN + lane * 4 + u, p.Skv - 1));
+        reinterpret_cast<float4*>(smem + C::SMEM_SK + s * (BN * 4))[lane] = make_float4(a[0], a[1], a[2], a[3]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->v_full[s]);
     };
     if (warp == C::NSOFT + 1) {
         if (lane < 4) {
@@ -482,6 +482,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 load_v(n);
             }
         }
+        if constexpr (TOKEN) {
+            if (!p.sk_bulk) {
+                griddep_wait();  // (every lane reads scale_k, which the quantiser of this call wrote)
+                __syncwarp();
+                for (int n = 0; n < n_pre; ++n) load_sk_warp(n);
+            }
+        }
     }
     if constexpr (C::MMASUM) {
         for (int i = threadIdx.x; i < C::ONES_BYTES / 4; i += C::NTHREADS)
@@ -502,7 +509,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if constexpr (C::REBALANCE) reg_dealloc<C::REG_OTHER>();
         if (warp == C::NSOFT + 1) {
             // =========================================================== TMA producer
-            if (lane == 0) {
+            if (TOKEN && !p.sk_bulk) {
+                // (unaligned per-token K scales: lane 0 runs the ring as below, the whole warp then fills the scale slot)
+                for (int n = n_pre; n < n_kv; ++n) {
+                    const int s = n % C::STAGES;
+                    const uint32_t ph = (n / C::STAGES) & 1;
+                    if (lane == 0) {
+                        mbar_wait(&bars->k_empty[s], ph ^ 1);
+                        load_kv(n);
+                        mbar_wait(&bars->v_empty[s], ph ^ 1);
+                        load_v(n);
+                    }
+                    __syncwarp();
+                    load_sk_warp(n);
+                }
+            } else if (lane == 0) {
                 for (int n = n_pre; n < n_kv; ++n) {  // (Q and the first n_pre tiles were issued during the setup)
                     const int s = n % C::STAGES;
                     const uint32_t ph = (n / C::STAGES) & 1;

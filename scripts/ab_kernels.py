@@ -8,9 +8,10 @@ tag = sys.argv[1] if len(sys.argv) > 1 else os.path.basename(os.environ.get("QA_
 dev = torch.device("cuda:0")
 PM = {"fp8": 0, "hilo": 1, "16bit": 2}
 shapes = [("C2", 24, 4608, 128, False), ("C3", 32, 8192, 128, True), ("d64", 32, 8192, 64, False), ("d64c", 32, 8192, 64, True),
-          ("d256", 16, 8192, 256, False), ("d256c", 16, 8192, 256, True), ("c4s", 4, 75600, 128, False)]
+          ("d256", 16, 8192, 256, False), ("d256c", 16, 8192, 256, True), ("c4s", 4, 75600, 128, False),
+          ("C2u", 24, 4606, 128, False)]  # C2u: S % 4 != 0 (token-wise: rows of scale_k not 16-byte aligned)
 modes = os.environ.get("AB_MODES", "16bit,fp8,hilo").split(",")
-only = os.environ.get("AB_SHAPES")
+only = os.environ.get("AB_SHAPES", "C2,C3,d64,d64c,d256,d256c,c4s")
 if only:
     shapes = [s for s in shapes if s[0] in only.split(",")]
 out = []
