@@ -31,6 +31,25 @@ def test_every_declared_symbol_is_exported():
         assert hasattr(lib, name), name
 
 
+def test_header_is_plain_c_and_the_c_example_compiles(tmp_path):
+    """The boundary is a C ABI: include/qattn.h must compile as C99 (no C++-isms, no CUDA / torch types), and the C
+    caller in examples/ must compile against it and link against the built library."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    src = os.path.join(ROOT, "examples", "c_abi_example.c")
+    obj = str(tmp_path / "ex.o")
+    subprocess.run([gcc, "-std=c99", "-fPIC", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), "-c", src, "-o", obj],
+                   check=True)
+    # every qa_ symbol the example uses resolves in the library
+    lib = build.build_library()
+    so = str(tmp_path / "libex.so")
+    subprocess.run([gcc, "-shared", "-o", so, obj, lib, "-Wl,--no-undefined"], check=True)
+
+
 def test_argument_validation_without_gpu():
     lib = _native.load()
     vp = ctypes.c_void_p
