@@ -1,5 +1,7 @@
 #!/bin/bash
 # A/B of the softmax schedule knobs and the per-warp arrival on the final kernel (kernel alone, one box)
+# variants first (here, no GPU): bash scripts/build_variant.sh tune_warparrive -DQA_WARP_ARRIVE=1; tune_loadq6 -DQA_LOADQ=6; tune_loadq10 -DQA_LOADQ=10;
+# tune_ldw2 -DQA_LDWAITQ=2; tune_ldw6 -DQA_LDWAITQ=6; tune_pubq4 -DQA_PUBQ=4; tune_poly3 -DQA_POLY_P16=3; tune_poly1 -DQA_POLY_P16=1; tune_dec2 -DQA_DECIDEQ=2
 mkdir -p gpurun_out
 L=$PWD/quantumattention_b200
 out=gpurun_out/r02_tune_ab.txt
